@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — one JSON line per run.
+
+A step = one pass of the hot path (element stiffness -> sort/reduce assembly -> Dirichlet
+elimination -> Jacobi-PCG to ||r||/||b|| <= 1e-9 -> reactions + stress) over one synthetic
+plate.  Default workload: BASELINE.json configs[3], the 16 M-DOF plate (4000 x 2000 cells).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nx NX --ny NY]
+
+`value`   whole-path Melem/s with the mesh already resident in HBM (device-generated plate),
+          timed with CUDA events on the launching stream, max over ranks;
+`e2e`     the same through mag_solve with pinned HOST buffers (H2D of the mesh and D2H of
+          ux,uy,fx,fy,stress inside the timed region);
+`roofline` the PCG SpMV kernel (SELL-32 + fused p.q): algorithmic bytes / CUDA-event time of
+          back-to-back launches of that kernel, against MEASURED_PEAKS.json hbm_gbs;
+`cpu_baseline` / `--impl reference`: the oracle port (oracle/magnetite_oracle.c, the reference's
+          arithmetic with CSR storage, 1 thread like the reference) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "whole-path Melem/s (assembly + PCG to 1e-9 + stress); also assembly Melem/s, PCG time-to-solve, SpMV HBM GB/s"
+UNIT = "Melem/s"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=4000)
+    ap.add_argument("--ny", type=int, default=2000)
+    ap.add_argument("--ref-nx", type=int, default=400, help="CPU sample plate (reference arm / cpu_baseline)")
+    ap.add_argument("--ref-ny", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--spmv-reps", type=int, default=100)
+    return ap.parse_args()
+
+
+def workload_name(nx, ny):
+    return f"synthetic structured plate {nx}x{ny} cells: {2 * nx * ny} CST triangles, " \
+           f"{2 * (nx + 1) * (ny + 1)} DOF, h=2, E=69e9, nu=0.33, t=0.5, left edge clamped, right edge ux=3"
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc = None
+        self.path = None
+        self.gpu = gpu_index
+        if shutil.which("nvidia-smi"):
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(gpu_index)], stdout=self.fh, stderr=subprocess.DEVNULL)
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in Path(self.path).read_text().splitlines():
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return None
+        # samples under load = the upper half (idle samples before/after drag the median down)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle port on a bounded sample
+# ---------------------------------------------------------------------------
+def cpu_sample(nx, ny):
+    """Whole path through the oracle's sparse mode (reference arithmetic, CSR storage, 1 thread) on a
+    smaller plate of the same family, solved to the same 1e-9 relative residual with the same
+    Jacobi-PCG.  Returns (Melem/s, seconds, stats)."""
+    from magnetite_b200 import meshgen
+    from oracle import oracle as O
+    mesh = meshgen.plate(nx, ny)
+    om = O.Mesh(mesh)
+    t0 = time.perf_counter()
+    res = O.run(om, meshgen.EXAMPLE_MATERIAL, O.cg_options(jacobi=1, rel_tol=1e-9), dense=False)
+    dt = time.perf_counter() - t0
+    return mesh.n_elems / dt / 1e6, dt, res["stats"]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nx, ny = args.ref_nx, args.ref_ny
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(max(nx // 4, 8), max(ny // 4, 4))
+    vals, secs, st = [], [], None
+    for _ in range(args.steps):
+        v, dt, st = cpu_sample(nx, ny)
+        vals.append(v); secs.append(dt)
+    value = statistics.mean(vals)
+    sample = (f"plate {nx}x{ny} cells ({2 * nx * ny} triangles) solved completely per step by the oracle port "
+              f"(reference arithmetic, CSR storage, Jacobi-PCG to 1e-9, {st['iters']} iterations); the 16M-DOF "
+              f"workload needs ~{args.nx / nx:.0f}x more CG iterations per element, so this favours the CPU")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(secs),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.nx, args.ny), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    from magnetite_b200 import _lib, meshgen
+    from magnetite_b200.solver import _material
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        raise SystemExit("multi-GPU bench: see bench_dist in a later commit")  # replaced below when dist lands
+    torch.cuda.set_device(local_rank)
+    lib = _lib.load()
+    ctx = _lib.Context(local_rank)
+    stream = torch.cuda.Stream()
+    meta = meshgen.EXAMPLE_MATERIAL
+    mat = _material(meta)
+    opt = _lib.default_options(stream=stream.cuda_stream)
+    nx, ny = args.nx, args.ny
+
+    # ---- device-resident workload ------------------------------------------------------
+    dm = C.c_void_p()
+    _lib.check(lib.mag_devmesh_plate(ctx.handle, nx, ny, 2.0, 3.0, C.byref(dm)), "mag_devmesh_plate")
+    view = _lib.MagMesh()
+    _lib.check(lib.mag_devmesh_view(dm, C.byref(view)), "mag_devmesh_view")
+    N, E = int(view.n_nodes), int(view.n_elems)
+    dev = torch.device("cuda", local_rank)
+    out_d = {k: torch.empty(N, dtype=torch.float64, device=dev) for k in ("ux", "uy", "fx", "fy")}
+    out_d["stress"] = torch.empty(E, dtype=torch.float64, device=dev)
+    res_d = _lib.MagResult(out_d["ux"].data_ptr(), out_d["uy"].data_ptr(), out_d["fx"].data_ptr(),
+                           out_d["fy"].data_ptr(), out_d["stress"].data_ptr(), None, 1)
+
+    def device_step():
+        st = _lib.MagStats()
+        _lib.check(lib.mag_solve(ctx.handle, C.byref(view), C.byref(mat), C.byref(opt), C.byref(res_d), C.byref(st)),
+                   "mag_solve(device)")
+        return st
+
+    for _ in range(args.warmup):
+        device_step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stats = []
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            stats.append(device_step())
+        ev1.record(stream)
+    torch.cuda.synchronize()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    ms_step = ms_total / args.steps
+    value = E / (ms_step * 1e-3) / 1e6
+    last = stats[-1]
+    launches = int(sum(s.kernel_launches for s in stats))
+    ms_asm = statistics.mean(s.ms_elem + s.ms_sort + s.ms_reduce + s.ms_bc for s in stats)
+    ms_solve = statistics.mean(s.ms_solve for s in stats)
+
+    # ---- roofline of the dominant kernel: the PCG SpMV, timed live ---------------------
+    sysh = C.c_void_p()
+    st = _lib.MagStats()
+    _lib.check(lib.mag_assemble(ctx.handle, C.byref(view), C.byref(mat), C.byref(opt), C.byref(sysh), C.byref(st)),
+               "mag_assemble")
+    ms_spmv, nbytes = C.c_float(), C.c_uint64()
+    _lib.check(lib.mag_system_spmv_bench(sysh, 2, args.spmv_reps, C.byref(ms_spmv), C.byref(nbytes)), "spmv_bench")
+    lib.mag_system_free(sysh)
+    peak, peak_src = measured_peak()
+    csr_bytes = int(last.spmv_bytes)
+    achieved = nbytes.value / (ms_spmv.value * 1e-3) / 1e9
+    iter_bytes = nbytes.value + 88 * int(last.n_free)
+    ms_iter = ms_solve / max(int(last.iters), 1)
+    roofline = {"bound": "hbm", "kernel": "pcg_spmv_kernel (SELL-32 SpMV + fused p.q)", "achieved": achieved,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "algorithmic_bytes_per_launch": int(nbytes.value),
+                "csr_equivalent_bytes": csr_bytes, "ms_per_launch": ms_spmv.value,
+                "pcg_iteration": {"bytes": iter_bytes, "ms": ms_iter,
+                                  "achieved": iter_bytes / (ms_iter * 1e-3) / 1e9,
+                                  "frac": iter_bytes / (ms_iter * 1e-3) / 1e9 / peak}}
+
+    # ---- end to end: pinned host buffers through mag_solve ----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = meshgen.plate(nx, ny)
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        hx, hy = pin(host.x), pin(host.y)
+        h0, h1, h2 = (pin(a.view(np.int32)) for a in (host.n0, host.n1, host.n2))
+        hux, huy, hfx, hfy, hk = pin(host.ux), pin(host.uy), pin(host.fx), pin(host.fy), pin(host.known)
+        hm = _lib.MagMesh(N, E, hx.data_ptr(), hy.data_ptr(), h0.data_ptr(), h1.data_ptr(), h2.data_ptr(),
+                          hux.data_ptr(), huy.data_ptr(), hfx.data_ptr(), hfy.data_ptr(), hk.data_ptr(), 0)
+        out_h = {k: torch.empty(N, dtype=torch.float64).pin_memory() for k in ("ux", "uy", "fx", "fy")}
+        out_h["stress"] = torch.empty(E, dtype=torch.float64).pin_memory()
+        res_h = _lib.MagResult(out_h["ux"].data_ptr(), out_h["uy"].data_ptr(), out_h["fx"].data_ptr(),
+                               out_h["fy"].data_ptr(), out_h["stress"].data_ptr(), None, 0)
+        h2d = N * (8 * 6 + 1) + E * 12
+        d2h = N * 32 + E * 8
+
+        def host_step():
+            s = _lib.MagStats()
+            _lib.check(lib.mag_solve(ctx.handle, C.byref(hm), C.byref(mat), C.byref(opt), C.byref(res_h), C.byref(s)),
+                       "mag_solve(host)")
+            return s
+
+        host_step()
+        torch.cuda.synchronize()
+        e_steps = max(1, min(args.steps, 2))
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for _ in range(e_steps):
+                host_step()
+            ev1.record(stream)
+        torch.cuda.synchronize()
+        ms_e2e = ev0.elapsed_time(ev1) / e_steps
+        e2e = {"value": E / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e_steps,
+               "checksum_ux_max": float(out_h["ux"].max())}
+
+    # ---- CPU baseline beside it ----------------------------------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, dt, cst = cpu_sample(args.ref_nx, args.ref_ny)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"plate {args.ref_nx}x{args.ref_ny} cells ({2 * args.ref_nx * args.ref_ny} triangles) solved "
+                         f"completely once by the oracle port (reference arithmetic, CSR storage, Jacobi-PCG to 1e-9, "
+                         f"{cst['iters']} iterations, {dt:.1f} s); iterations grow ~7.3*nx, so per element the "
+                         f"{nx}x{ny} workload costs the CPU ~{nx / args.ref_nx:.0f}x more",
+               "seconds": dt, "host_cores_available": os.cpu_count()}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(nx, ny), "parallelism": "1 GPU",
+                   "l2": "inputs larger than L2 (K_ff + vectors >> 126 MB), no flush needed",
+                   "solver": "Jacobi-PCG, rel_tol 1e-9, SELL-32 SpMV", "n_free": int(last.n_free),
+                   "nnz": int(last.nnz), "nnz_structural": int(last.nnz_structural)},
+        "metrics": {"assembly_melem_s": E / (ms_asm * 1e-3) / 1e6, "assembly_ms": ms_asm,
+                    "pcg_time_to_solve_s": ms_solve * 1e-3, "pcg_iters": int(last.iters),
+                    "pcg_final_rel_residual": last.final_residual / last.b_norm if last.b_norm else 0.0,
+                    "spmv_hbm_gbs": achieved, "ms_elem": last.ms_elem, "ms_sort": last.ms_sort,
+                    "ms_reduce": last.ms_reduce, "ms_bc": last.ms_bc, "ms_format": last.ms_format,
+                    "ms_post": last.ms_post},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    lib.mag_devmesh_free(dm)
+    ctx.close()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,188 @@
+/*
+ * magnetite_b200.h — C ABI of the B200-native replacement for Magnetite's
+ * numerical core (libmagnetite_b200.so, CUDA sm_100a, fp64).
+ *
+ * This is the drop-in boundary for everything inside the reference's
+ *     solver::run(&mut Vec<Node>, &mut Vec<Element>, &ModelMetadata)
+ *         -> Result<(), MagnetiteError>                  (src/solver.rs:543-586)
+ * plus the pieces of it that other reference modules call directly
+ * (solver::compute_element_area, used by mesher::check_ccw, src/mesher.rs:522-526).
+ * The Rust side keeps its own structs; a thin shim (rust/)
+ * flattens Vec<Node>/Vec<Element> (src/datatypes.rs:2-20) into the SoA arrays
+ * below, calls mag_solve and writes the results back as Some(..).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; the caller owns every buffer it passes and
+ *    the library keeps no pointer past the call (device scratch lives in the
+ *    mag_ctx / mag_system handles and is freed with them);
+ *  - every function returns 0 (MAG_OK) or a negative MAG_ERR_* code and never
+ *    aborts or throws across the boundary; mag_last_error() gives the
+ *    thread-local message, which the shim wraps in MagnetiteError::Solver
+ *    (src/error.rs:4-22; src/solver.rs:160-164);
+ *  - there is no CPU fallback: without a CUDA device every compute entry
+ *    point fails with MAG_ERR_CUDA.
+ */
+#ifndef MAGNETITE_B200_H
+#define MAGNETITE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAG_ABI_VERSION 1
+
+/* src/solver.rs:17-19 */
+#define MAG_DOF 2
+#define MAG_MAX_CG_ITER 10000000ull
+#define MAG_TARGET_CG_COST 1e-4
+
+enum {
+    MAG_OK = 0,
+    MAG_ERR_CUDA = -1,          /* CUDA runtime failure / no device            */
+    MAG_ERR_OOM = -2,           /* device or host allocation failed            */
+    MAG_ERR_BAD_BC = -3,        /* #rows with known force != #unknown displ.   *
+                                 * (the reference panics: solver.rs:380-396)   */
+    MAG_ERR_BAD_INDEX = -4,     /* element references a node >= n_nodes        */
+    MAG_ERR_INDEFINITE = -5,    /* p.Ap == 0 or NaN during CG                  */
+    MAG_ERR_NOT_CONVERGED = -6, /* max_iter reached (results still written)    */
+    MAG_ERR_NCCL = -7,
+    MAG_ERR_BAD_ARG = -8
+};
+
+/* which Option<f64> fields of Node (src/datatypes.rs:8-14) are Some(..) */
+#define MAG_KNOWN_UX 1u
+#define MAG_KNOWN_UY 2u
+#define MAG_KNOWN_FX 4u
+#define MAG_KNOWN_FY 8u
+
+/* Vec<Node> + Vec<Element> flattened to SoA.  Replaces the `nodes`/`elements`
+ * arguments of solver::run (src/solver.rs:544-545). */
+typedef struct {
+    uint64_t n_nodes, n_elems;
+    const double *x, *y;               /* node.vertex.{x,y}                      */
+    const uint32_t *n0, *n1, *n2;      /* element.nodes[0..3], 0-based           */
+    const double *ux, *uy, *fx, *fy;   /* payload of Some(..) (ignored if None)  */
+    const uint8_t *known;              /* MAG_KNOWN_* per node                   */
+    int32_t on_device;                 /* 0: host pointers; 1: device pointers   */
+} mag_mesh;
+
+/* ModelMetadata (src/datatypes.rs:23-29; CL fields are unused by the solver). */
+typedef struct {
+    double youngs_modulus, poisson_ratio, part_thickness;
+} mag_material;
+
+/* Solver knobs.  The reference has compile-time constants only
+ * (src/solver.rs:18-19, 143, 153-154); compat=1 reproduces them. */
+typedef struct {
+    double rel_tol;          /* stop at ||r||_2 <= rel_tol*||b||_2   (default 1e-9)   */
+    double abs_tol;          /* compat target cost                   (default 1e-4)   */
+    uint64_t max_iter;       /* default 1e7                                            */
+    int32_t precond;         /* 0 none, 1 Jacobi (default)                             */
+    int32_t compat;          /* 1: reference semantics — plain CG, x0=0, absolute cost */
+    int32_t cost_kind;       /* compat cost: 0 = ||r||_2 (default), 1 = r.r            */
+    int32_t drop_exact_zeros;/* 1 (default): K_ff keeps k != 0.0 only (solver.rs:132)  */
+    int32_t check_every;     /* iterations per CUDA-graph chunk between residual polls */
+    int32_t spmv_format;     /* 0 auto, 1 scalar CSR, 2 SELL-32                        */
+    int32_t want_sigma;      /* also return sx,sy,txy per element                      */
+    int32_t reserved;
+    void *stream;            /* cudaStream_t to run on, or NULL for the ctx's own      */
+} mag_options;
+
+/* Outputs of solver::run: every node gets ux,uy,fx,fy = Some (solver.rs:476-482),
+ * every element gets stress = Some (solver.rs:532-533).  Caller-allocated. */
+typedef struct {
+    double *ux, *uy, *fx, *fy;         /* n_nodes each                            */
+    double *stress;                    /* n_elems                                 */
+    double *sigma;                     /* optional n_elems*3 (sx,sy,txy) or NULL  */
+    int32_t on_device;
+} mag_result;
+
+typedef struct {
+    uint64_t n_nodes, n_elems, n_dof, n_free, n_constrained;
+    uint64_t nnz_structural;           /* stored entries of the full K (2x2 BSR)  */
+    uint64_t nnz;                      /* stored entries of K_ff                   */
+    uint64_t sell_entries;             /* padded entries of the SELL-32 copy       */
+    uint64_t iters;                    /* CG iterations (solver.rs:101-104)        */
+    double final_residual;             /* ||r||_2 at exit (recursive residual)     */
+    double b_norm;                     /* ||b||_2                                  */
+    int32_t converged;
+    int32_t negative_definite;         /* all-clockwise mesh           */
+    /* device time per phase, milliseconds (CUDA events on the run stream) */
+    float ms_upload, ms_elem, ms_sort, ms_reduce, ms_bc, ms_format, ms_solve,
+          ms_post, ms_download, ms_total;
+    uint64_t kernel_launches;          /* launches issued by this call             */
+    uint64_t spmv_bytes;               /* algorithmic bytes of one SpMV            */
+} mag_stats;
+
+typedef struct mag_ctx mag_ctx;        /* device + stream + memory pool + comm    */
+typedef struct mag_system mag_system;  /* assembled K, K_ff, rhs, maps on device  */
+
+/* ---- lifecycle ----------------------------------------------------------- */
+int mag_abi_version(void);
+const char *mag_last_error(void);
+int mag_device_count(int *count);
+int mag_ctx_create(mag_ctx **ctx, int device);
+void mag_ctx_destroy(mag_ctx *ctx);
+void mag_options_default(mag_options *opt);
+
+/* ---- the drop-in call: replaces solver::run (src/solver.rs:543-586) ------ */
+int mag_solve(mag_ctx *ctx, const mag_mesh *mesh, const mag_material *mat,
+              const mag_options *opt, mag_result *out, mag_stats *stats);
+
+/* ---- phase-level entry points (bench + parity) --------------------------- */
+/* element stiffness + COO sort + segmented reduce + BC elimination; replaces
+ * solver.rs:549-572 and :420-432 (build_col_vecs .. rhs). */
+int mag_assemble(mag_ctx *ctx, const mag_mesh *mesh, const mag_material *mat,
+                 const mag_options *opt, mag_system **sys, mag_stats *stats);
+/* CG on the assembled system + scatter + reactions + stress; replaces
+ * solver.rs:435-482 and :578-583. */
+int mag_system_solve(mag_system *sys, const mag_options *opt, mag_result *out, mag_stats *stats);
+void mag_system_free(mag_system *sys);
+int mag_system_info(const mag_system *sys, mag_stats *stats);
+
+/* parity exports (host buffers, caller-allocated from mag_system_info sizes) */
+int mag_system_export_kff(const mag_system *sys, int64_t *rowptr /*n_free+1*/, int32_t *col,
+                          double *val, double *rhs /*n_free*/, int64_t *free_map /*n_dof*/);
+int mag_system_export_full(const mag_system *sys, int64_t *rowptr /*n_dof+1*/, int32_t *col,
+                           double *val /*nnz_structural*/);
+/* K_e for every element, row-major 6x6 (solver.rs:263-278); host output. */
+int mag_element_stiffness(mag_ctx *ctx, const mag_mesh *mesh, const mag_material *mat,
+                          double *ke /* n_elems*36 */);
+/* signed areas (solver.rs:187-193, pub: used by mesher::check_ccw). */
+int mag_element_area(mag_ctx *ctx, const mag_mesh *mesh, double *area /* n_elems */);
+/* stress recovery only (solver.rs:496-535). */
+int mag_stress(mag_ctx *ctx, const mag_mesh *mesh, const mag_material *mat, const double *ux,
+               const double *uy, double *stress, double *sigma /*or NULL*/);
+/* y = K_ff x on host vectors (parity) and timed device loop (roofline). */
+int mag_system_spmv(mag_system *sys, int format, const double *x, double *y);
+int mag_system_spmv_bench(mag_system *sys, int format, int reps, float *ms_per_spmv,
+                          uint64_t *algorithmic_bytes);
+
+/* ---- synthetic meshes generated on the device ------------- */
+/* Plate(nx,ny,h): node (i,j) -> id j*(nx+1)+i at (i*h, j*h); cell -> [a,b,d],[a,d,c];
+ * left edge clamped, right edge ux=ux_right, fy=0.  All outputs are device
+ * buffers owned by the returned mesh handle. */
+typedef struct mag_devmesh mag_devmesh;
+int mag_devmesh_plate(mag_ctx *ctx, uint32_t nx, uint32_t ny, double h, double ux_right,
+                      mag_devmesh **out);
+int mag_devmesh_view(const mag_devmesh *dm, mag_mesh *view);
+void mag_devmesh_free(mag_devmesh *dm);
+
+/* ---- multi-GPU: one process per GPU, contiguous row blocks --------------- */
+int mag_comm_unique_id(void *id128 /* 128 bytes out */);
+int mag_comm_init(mag_ctx *ctx, int rank, int nranks, const void *id128);
+int mag_comm_rank(const mag_ctx *ctx, int *rank, int *nranks);
+/* node range [lo,hi) owned by `rank` of `nranks` for a mesh of n_nodes */
+int mag_partition_nodes(uint64_t n_nodes, int nranks, int rank, uint64_t *lo, uint64_t *hi);
+
+/* ---- debug entry points used by the GPU unit tests ----------------------- */
+int mag_debug_sort_pairs(mag_ctx *ctx, uint64_t *keys, uint32_t *payload, uint64_t n, int key_bits);
+int mag_debug_exclusive_scan(mag_ctx *ctx, const uint32_t *in, uint32_t *out /*n+1*/, uint64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

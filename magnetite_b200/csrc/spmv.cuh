@@ -1,0 +1,212 @@
+// spmv.cuh — y = K_ff x in fp64 (replaces `&CsrMatrix * DVector`, reference
+// src/solver.rs:31-36, nalgebra-sparse spmm_csr_dense).
+//
+// Two device formats of the same matrix:
+//   CSR      rowptr u32 / col i32 / val f64 — the assembly product and the
+//            parity artefact (bit-exact pattern vs the reference's CSR);
+//   SELL-32  the solver format: rows in slices of 32 (one warp), stored
+//            column-major inside the slice and padded to the slice's longest
+//            row, so lane l of a warp streams val/col at base + k*32 + l —
+//            every load instruction of the val and col streams is one fully
+//            coalesced 256 B / 128 B request.  The x gathers go through L1/L2
+//            (ld.global.nc): neighbouring rows of a mesh matrix touch
+//            neighbouring columns, so they coalesce too.
+// The SpMV that runs inside CG also produces the partial dot product p.q, so q
+// is not re-read for it.
+#pragma once
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace mag {
+
+struct CsrMatrix {                 // local rows [row_lo, row_lo+n_rows) x global cols
+    uint32_t n_rows = 0, row_lo = 0;
+    uint64_t n_cols = 0, nnz = 0;
+    DevBuf<uint32_t> rowptr;       // n_rows+1
+    DevBuf<int32_t> col;
+    DevBuf<double> val;
+};
+
+struct SellMatrix {
+    uint32_t n_rows = 0, n_slices = 0, row_lo = 0;
+    uint64_t entries = 0;          // padded entries (multiple of 32)
+    DevBuf<uint32_t> slice_off;    // n_slices+1, in units of 32 entries
+    DevBuf<int32_t> col;
+    DevBuf<double> val;
+};
+
+// ---- CSR -> SELL-32 --------------------------------------------------------
+__global__ void sell_width_kernel(const uint32_t *__restrict__ rowptr, uint32_t n_rows,
+                                  uint32_t n_slices, uint32_t *__restrict__ width) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t len = (row < n_rows) ? rowptr[row + 1] - rowptr[row] : 0u;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, off));
+    const uint32_t s = row >> 5;
+    if ((threadIdx.x & 31) == 0 && s < n_slices) width[s] = len;
+}
+
+__global__ void sell_fill_kernel(const uint32_t *__restrict__ rowptr, const int32_t *__restrict__ ccol,
+                                 const double *__restrict__ cval, uint32_t n_rows, uint32_t row_lo,
+                                 const uint32_t *__restrict__ slice_off, int32_t *__restrict__ scol,
+                                 double *__restrict__ sval) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t s = row >> 5, lane = threadIdx.x & 31;
+    // whole warps stay together: a slice is written by the warp that owns it
+    const uint32_t n_slices = (n_rows + 31) >> 5;
+    if (s >= n_slices) return;
+    const uint32_t w = slice_off[s + 1] - slice_off[s];
+    const size_t base = (size_t)slice_off[s] * 32 + lane;
+    const uint32_t p0 = (row < n_rows) ? rowptr[row] : 0u;
+    const uint32_t len = (row < n_rows) ? rowptr[row + 1] - p0 : 0u;
+    // padding multiplies 0.0 by x at a column that is always valid and cached
+    const int32_t pad_col = (int32_t)(row_lo + (row < n_rows ? row : n_rows - 1));
+    for (uint32_t k = 0; k < w; ++k) {
+        const bool real = k < len;
+        scol[base + (size_t)k * 32] = real ? ccol[p0 + k] : pad_col;
+        sval[base + (size_t)k * 32] = real ? cval[p0 + k] : 0.0;
+    }
+}
+
+inline void build_sell(mag_ctx *ctx, const CsrMatrix &A, SellMatrix &S) {
+    S.n_rows = A.n_rows; S.row_lo = A.row_lo;
+    S.n_slices = (A.n_rows + 31) / 32;
+    S.slice_off.alloc(ctx, (size_t)S.n_slices + 1);
+    if (S.n_slices == 0) { S.entries = 0; S.slice_off.zero(); S.col.alloc(ctx, 0); S.val.alloc(ctx, 0); return; }
+    const unsigned blocks = cdiv((size_t)S.n_slices * 32, 256);
+    MAG_LAUNCH(ctx, sell_width_kernel, blocks, 256, 0, (const uint32_t *)A.rowptr.p, A.n_rows,
+               S.n_slices, S.slice_off.p);
+    exclusive_scan_u32(ctx, S.slice_off.p, S.n_slices, S.slice_off.p, (size_t)S.n_slices + 1);
+    uint32_t groups = 0;
+    MAG_CUDA(cudaMemcpyAsync(&groups, S.slice_off.p + S.n_slices, sizeof(uint32_t),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+    S.entries = (uint64_t)groups * 32;
+    S.col.alloc(ctx, S.entries);
+    S.val.alloc(ctx, S.entries);
+    MAG_LAUNCH(ctx, sell_fill_kernel, blocks, 256, 0, (const uint32_t *)A.rowptr.p,
+               (const int32_t *)A.col.p, (const double *)A.val.p, A.n_rows, A.row_lo,
+               (const uint32_t *)S.slice_off.p, S.col.p, S.val.p);
+}
+
+// ---- deterministic grid-wide sums ------------------------------------------
+// Every CTA writes its partial sum(s); the last CTA to arrive (ticket counter)
+// adds all partials in a fixed order, so the result does not depend on which
+// CTA happens to be last.  NV = number of simultaneous sums (1 or 2).
+template <int NV>
+__device__ __forceinline__ bool grid_sum_256(double (&v)[NV], double *__restrict__ partials,
+                                             unsigned *__restrict__ ticket, double (&total)[NV]) {
+    __shared__ double red[NV][8];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+        if (lane == 0) red[i][warp] = v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += red[i][w];
+            partials[(size_t)i * gridDim.x + blockIdx.x] = s;
+        }
+        __threadfence();
+        const unsigned t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double s = 0.0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += 256)
+            s += __ldcg(&partials[(size_t)i * gridDim.x + b]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) red[i][warp] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += red[i][w];
+            total[i] = s;
+        }
+        *ticket = 0;      // ready for the next launch
+    }
+    return threadIdx.x == 0;
+}
+
+// ---- SELL-32 SpMV ----------------------------------------------------------
+// One warp per slice, grid-stride over slices.  x is indexed by global column;
+// y by local row.  If DOT, also accumulates sum_i x[row_lo+i]*y[i].
+template <bool DOT>
+__device__ __forceinline__ double sell_rows(const uint32_t *__restrict__ slice_off,
+                                            const int32_t *__restrict__ scol,
+                                            const double *__restrict__ sval,
+                                            const double *__restrict__ x, double *__restrict__ y,
+                                            uint32_t n_rows, uint32_t n_slices, uint32_t row_lo) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    double dot = 0.0;
+    for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slices; s += warps) {
+        const uint32_t o0 = __ldg(&slice_off[s]), o1 = __ldg(&slice_off[s + 1]);
+        const double *v = sval + (size_t)o0 * 32 + lane;
+        const int32_t *c = scol + (size_t)o0 * 32 + lane;
+        const uint32_t w = o1 - o0;
+        double acc0 = 0.0, acc1 = 0.0;
+        uint32_t k = 0;
+        for (; k + 4 <= w; k += 4) {
+            const double a0 = __ldcs(v + (size_t)(k + 0) * 32), a1 = __ldcs(v + (size_t)(k + 1) * 32);
+            const double a2 = __ldcs(v + (size_t)(k + 2) * 32), a3 = __ldcs(v + (size_t)(k + 3) * 32);
+            const int32_t c0 = __ldcs(c + (size_t)(k + 0) * 32), c1 = __ldcs(c + (size_t)(k + 1) * 32);
+            const int32_t c2 = __ldcs(c + (size_t)(k + 2) * 32), c3 = __ldcs(c + (size_t)(k + 3) * 32);
+            const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+            acc0 = fma(a0, x0, acc0); acc1 = fma(a1, x1, acc1);
+            acc0 = fma(a2, x2, acc0); acc1 = fma(a3, x3, acc1);
+        }
+        for (; k < w; ++k) acc0 = fma(__ldcs(v + (size_t)k * 32), __ldg(x + __ldcs(c + (size_t)k * 32)), acc0);
+        const uint32_t row = s * 32 + lane;
+        if (row < n_rows) {
+            const double yi = acc0 + acc1;
+            y[row] = yi;
+            if (DOT) dot = fma(__ldg(x + row_lo + row), yi, dot);
+        }
+    }
+    return dot;
+}
+
+__global__ void __launch_bounds__(256, 6)
+spmv_sell_kernel(const uint32_t *__restrict__ slice_off, const int32_t *__restrict__ scol,
+                 const double *__restrict__ sval, const double *__restrict__ x,
+                 double *__restrict__ y, uint32_t n_rows, uint32_t n_slices, uint32_t row_lo) {
+    (void)sell_rows<false>(slice_off, scol, sval, x, y, n_rows, n_slices, row_lo);
+}
+
+// ---- scalar CSR SpMV (thread per row; parity path and format comparison) ---
+__global__ void __launch_bounds__(256)
+spmv_csr_kernel(const uint32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
+                uint32_t n_rows) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    double acc = 0.0;
+    for (uint32_t p = rowptr[row]; p < rowptr[row + 1]; ++p)
+        acc = __dadd_rn(acc, __dmul_rn(val[p], __ldg(x + col[p])));   // reference order, no FMA
+    y[row] = acc;
+}
+
+inline unsigned sell_grid(const mag_ctx *ctx, uint32_t n_slices) {
+    const unsigned need = cdiv(n_slices, 8);
+    const unsigned cap = (unsigned)ctx->sm_count * 6u;
+    return need < cap ? (need ? need : 1u) : cap;
+}
+
+}  // namespace mag

@@ -1,0 +1,157 @@
+"""CPU: the C-ABI library loads and exports every symbol include/magnetite_b200.h declares, the
+product fails loudly without a GPU (no CPU fallback), and the host-side mirrors of the
+reference interface (datatypes, error, mesher BC rules, csv_output) behave like the reference."""
+import ctypes as C
+import json
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from magnetite_b200 import _lib, mesher, meshgen, post_processor
+from magnetite_b200.datatypes import Element, MeshSoA, Node, Vertex
+from magnetite_b200.error import MagnetiteError
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLDEN = ROOT / "tests" / "golden"
+
+
+def header_symbols():
+    text = (ROOT / "include" / "magnetite_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mag_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    lib = _lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+    assert sorted(_lib.declared_symbols()) == syms, "ctypes prototypes drifted from the header"
+    assert lib.mag_abi_version() == 1
+
+
+def test_struct_layouts_match_header(built):
+    # sizes computed by hand from include/magnetite_b200.h (LP64)
+    assert C.sizeof(_lib.MagMesh) == 2 * 8 + 10 * 8 + 8
+    assert C.sizeof(_lib.MagMaterial) == 24
+    assert C.sizeof(_lib.MagOptions) == 8 + 8 + 8 + 8 * 4 + 8
+    assert C.sizeof(_lib.MagResult) == 6 * 8 + 8
+    o = _lib.default_options()
+    assert (o.rel_tol, o.abs_tol, o.max_iter, o.precond, o.compat, o.drop_exact_zeros) == (1e-9, 1e-4, 10_000_000, 1, 0, 1)
+
+
+def test_no_cpu_fallback(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(MagnetiteError) as ei:
+        _lib.Context(0)
+    assert ei.value.kind == "Solver" and ei.value.code == _lib.MAG_ERR_CUDA
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_product_never_imports_oracle():
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|magnetite_oracle|liboracle|orc_[a-z]+\(", re.M)
+    files = [p for p in (ROOT / "magnetite_b200").rglob("*") if p.suffix in (".py", ".cu", ".cuh", ".h")]
+    assert len(files) > 10
+    for path in files:
+        assert not pat.search(path.read_text(errors="ignore")), f"{path} references the oracle"
+
+
+def test_partition_nodes(built):
+    lib = _lib.load()
+    lo, hi = C.c_uint64(), C.c_uint64()
+    covered = []
+    for r in range(8):
+        assert lib.mag_partition_nodes(8006001, 8, r, C.byref(lo), C.byref(hi)) == 0
+        covered.append((lo.value, hi.value))
+    assert covered[0][0] == 0 and covered[-1][1] == 8006001
+    assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    sizes = [b - a for a, b in covered]
+    assert max(sizes) - min(sizes) <= 1
+    assert lib.mag_partition_nodes(10, 0, 0, C.byref(lo), C.byref(hi)) == _lib.MAG_ERR_BAD_ARG
+
+
+def test_error_display_matches_reference():
+    assert str(MagnetiteError.Solver("boom")) == "Solver error: boom"
+    assert str(MagnetiteError.PostProcessor("x")) == "Post Processor error: x"
+    assert str(MagnetiteError.Input("x")) == "Input error: x"
+    assert str(MagnetiteError.Mesher("x")) == "Mesher error: x"
+
+
+def test_rust_display_formatting():
+    f = post_processor.rust_f64_display
+    assert f(3.0) == "3" and f(-0.0) == "-0" and f(0.0) == "0"
+    assert f(69e9) == "69000000000" and f(1e-7) == "0.0000001"
+    assert f(0.1 + 0.2) == "0.30000000000000004" and f(-4.5) == "-4.5"
+    assert f(1e21) == "1000000000000000000000" and f(1.5e-10) == "0.00000000015"
+    assert f(float("nan")) == "NaN" and f(float("inf")) == "inf" and f(float("-inf")) == "-inf"
+    for v in np.random.default_rng(0).normal(size=200) * 10.0 ** np.random.default_rng(1).integers(-12, 12, 200):
+        assert float(f(v)) == v and "e" not in f(v)
+
+
+def test_csv_output_format(tmp_path):
+    nodes = [Node(Vertex(0.0, 4.5), 0.0, -0.0, 1.0, 2.0), Node(Vertex(-11.0, 0.1), 3.0, 1e-7, 0.0, 0.0)]
+    els = [Element([1, 0, 1], -345000000.0)]
+    a, b = tmp_path / "nodes.csv", tmp_path / "elements.csv"
+    post_processor.csv_output(els, nodes, str(a), str(b), quiet=True)
+    assert a.read_bytes() == b"x,y,ux,uy\n0,4.5,0,-0\n-11,0.1,3,0.0000001\n"
+    assert b.read_bytes() == b"n0,n1,n2,stress\n1,0,1,-345000000\n"
+    with pytest.raises(MagnetiteError):
+        post_processor.csv_output(els, nodes, str(tmp_path / "nope" / "n.csv"), str(b), quiet=True)
+    with pytest.raises(MagnetiteError):
+        post_processor.csv_output([Element([0, 1, 0])], nodes, str(a), str(b), quiet=True)
+
+
+def test_boundary_rules_follow_the_code_not_the_docs():
+    data = mesher.load_input_file(str(GOLDEN / "tensile_input.json"))
+    meta = mesher.parse_input_metadata(data)
+    assert (meta.youngs_modulus, meta.poisson_ratio, meta.part_thickness) == (69e9, 0.33, 0.5)
+    xs = [-11.0, -10.0, -9.0, 0.0, 10.0, 10.5, 12.0]
+    nodes = mesher.default_nodes(xs, [0.0] * len(xs))
+    assert nodes[0].ux is None and nodes[0].fx == 0.0                    # mesher.rs:615-624
+    mesher.apply_boundary_conditions(data, nodes)
+    assert (nodes[0].ux, nodes[0].uy, nodes[0].fx, nodes[0].fy) == (0.0, 0.0, None, None)
+    assert nodes[1].ux is None and nodes[1].fx == 0.0                    # x == x_max: strict <, not selected
+    assert nodes[4].ux is None                                           # x == x_min: strict >
+    assert (nodes[5].ux, nodes[5].uy, nodes[5].fx, nodes[5].fy) == (3.0, None, None, 0.0)
+    assert nodes[6].ux is None
+    soa = MeshSoA.from_aos(nodes, [])
+    assert list(soa.known) == [3, 12, 12, 12, 12, 9, 12]
+    n2, _ = soa.to_aos()
+    assert n2[5].ux == 3.0 and n2[5].uy is None
+
+
+def test_boundary_rule_validation(tmp_path):
+    base = json.loads((GOLDEN / "tensile_input.json").read_text())
+    bad = json.loads(json.dumps(base)); bad["boundary_conditions"]["load"]["targets"]["fx"] = 1.0
+    with pytest.raises(MagnetiteError, match="over-constrained in x-axis"):
+        mesher.parse_boundary_rules(bad)
+    bad = json.loads(json.dumps(base)); bad["boundary_conditions"]["load"]["targets"]["fy"] = None
+    with pytest.raises(MagnetiteError, match="under-constrained in y-axis"):
+        mesher.parse_boundary_rules(bad)
+    bad = json.loads(json.dumps(base)); bad["boundary_conditions"]["load"]["region"]["x_target_min"] = 99
+    with pytest.raises(MagnetiteError, match="x_target_min greater"):
+        mesher.parse_boundary_rules(bad)
+    p = tmp_path / "x.json"; p.write_text("{\"metadata\": {}}")
+    with pytest.raises(MagnetiteError, match="boundary_conditions"):
+        mesher.load_input_file(str(p))
+    with pytest.raises(MagnetiteError, match="Unable to open"):
+        mesher.load_input_file(str(tmp_path / "missing.json"))
+
+
+def test_meshgen_invariants():
+    m = meshgen.plate(1000, 500)
+    assert m.n_elems == 1_000_000 and m.n_nodes == 501_501
+    m = meshgen.plate(7, 5)
+    x, y = m.x, m.y
+    a = 0.5 * (x[m.n0] * (y[m.n1] - y[m.n2]) + x[m.n1] * (y[m.n2] - y[m.n0]) + x[m.n2] * (y[m.n0] - y[m.n1]))
+    assert (a == 2.0).all()                                              # CCW, area >= 1: check_ccw no-op
+    p = meshgen.perforated_plate(64, 32, pitch=16, radius=4)
+    used = np.zeros(p.n_nodes, bool); used[p.n0] = used[p.n1] = used[p.n2] = True
+    assert used.all() and p.n_elems < 2 * 64 * 32
+    j = meshgen.jitter(m)
+    assert (j.x != m.x).any() and np.array_equal(j.known, m.known)

@@ -1,0 +1,279 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the oracle and the golden fixtures.
+
+Bars (BASELINE.json north_star): CSR sparsity pattern and DOF numbering bit-exact; K_e within
+1e-12 relative (measured per element as max|dK|/max|K|); displacements within 1e-9 relative L2;
+stresses within 1e-8 relative (|ds|_inf/|s|_inf).  Where the device follows the reference's
+operation order exactly (K_e, full K, K_ff, rhs, reactions and stresses given u) the tests also
+demand bit equality.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from magnetite_b200 import _lib, meshgen, solver
+from magnetite_b200.datatypes import Element, MeshSoA, Node, Vertex
+from magnetite_b200.error import MagnetiteError
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+META = meshgen.EXAMPLE_MATERIAL
+GOLDEN = Path(__file__).resolve().parent / "golden"
+GOLDEN_CASES = ["patch_2x2", "plate_8x6", "plate_jitter_10x7", "perforated_24x16", "clockwise_unit",
+                "clockwise_force"]
+
+
+def golden_mesh(g):
+    return MeshSoA(g["x"], g["y"], g["n0"], g["n1"], g["n2"], g["bc_ux"], g["bc_uy"], g["bc_fx"], g["bc_fy"], g["known"])
+
+
+def rel_l2(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def ke_rel(ke, ref):
+    scale = np.abs(ref).max(axis=(1, 2))
+    return (np.abs(ke - ref).max(axis=(1, 2)) / scale).max()
+
+
+def compat():
+    return _lib.default_options(compat=1)
+
+
+MESHES = {
+    "plate_20x10": lambda: meshgen.plate(20, 10),
+    "plate_33x17_h0.3": lambda: meshgen.plate(33, 17, h=0.3),       # non-representable coordinates
+    "jitter_31x19": lambda: meshgen.jitter(meshgen.plate(31, 19)),
+    "perforated_96x48": lambda: meshgen.perforated_plate(96, 48, pitch=16, radius=4),
+    "plate_257x65": lambda: meshgen.plate(257, 65),                 # > one sort tile per pass, ragged slices
+}
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_against_golden_fixtures(ctx, name):
+    g = np.load(GOLDEN / f"{name}.npz")
+    mesh = golden_mesh(g)
+    ke = solver.element_stiffness(mesh, META, ctx)
+    assert ke_rel(ke, g["ke"]) < 1e-12
+    assert np.array_equal(ke, g["ke"]), "K_e is expected to be bit-identical"
+    with solver.System(mesh, META, ctx) as S:
+        rp, col, val = S.export_full()
+        assert np.array_equal(rp, g["full_rowptr"]) and np.array_equal(col, g["full_col"])
+        assert np.array_equal(val, g["full_val"])
+        rp, col, val, rhs, fmap = S.export_kff()
+        assert np.array_equal(rp, g["kff_rowptr"]) and np.array_equal(col, g["kff_col"])   # pattern: bit-exact
+        assert np.array_equal(fmap, g["free_map"])                                          # DOF numbering
+        assert np.array_equal(val, g["kff_val"]) and np.array_equal(rhs, g["rhs"])
+        sol = S.solve(compat())
+    u, ur = np.concatenate([sol.ux, sol.uy]), np.concatenate([g["ux"], g["uy"]])
+    assert rel_l2(u, ur) < 1e-9
+    assert np.abs(sol.stress - g["stress"]).max() / np.abs(g["stress"]).max() < 1e-8
+    assert np.array_equal(np.sign(sol.stress), np.sign(g["stress"]))
+    f, fr = np.concatenate([sol.fx, sol.fy]), np.concatenate([g["fx"], g["fy"]])
+    assert np.abs(f - fr).max() / np.abs(fr).max() < 1e-8
+
+
+@pytest.mark.parametrize("name", list(MESHES))
+def test_pipeline_against_oracle(ctx, name):
+    mesh = MESHES[name]()
+    om = O.Mesh(mesh)
+    ke_ref = O.element_stiffness(om, META)
+    ke = solver.element_stiffness(mesh, META, ctx)
+    assert ke_rel(ke, ke_ref) < 1e-12 and np.array_equal(ke, ke_ref)
+    assert np.array_equal(solver.element_areas(mesh, ctx), O.element_area(om))
+    full_ref = O.assemble_sparse(om, ke_ref)
+    (rp_r, col_r, val_r), rhs_r, fmap_r = O.partition(om, full_ref, dense=False)
+    with solver.System(mesh, META, ctx) as S:
+        full = S.export_full()
+        for a, b in zip(full, full_ref):
+            assert np.array_equal(a, b)
+        rp, col, val, rhs, fmap = S.export_kff()
+        assert np.array_equal(rp, rp_r) and np.array_equal(col, col_r) and np.array_equal(fmap, fmap_r)
+        assert np.array_equal(val, val_r) and np.array_equal(rhs, rhs_r)
+        assert S.nnz == len(val_r) and S.nnz_structural == len(full_ref[2])
+        # SpMV: both device formats against the oracle's sequential row sums
+        x = np.random.default_rng(3).normal(size=S.n_free)
+        y_ref = O.spmv((rp_r, col_r, val_r), x)
+        assert np.array_equal(S.spmv(x, fmt=1), y_ref)                     # CSR kernel keeps the order
+        assert rel_l2(S.spmv(x, fmt=2), y_ref) < 1e-14                     # SELL uses FMA
+        ref = O.run(om, META, O.cg_options(), dense=False)
+        sol = S.solve(compat(), want_sigma=True)
+        sol_csr = S.solve(_lib.default_options(compat=1, spmv_format=1))
+    u, ur = np.concatenate([sol.ux, sol.uy]), np.concatenate([ref["ux"], ref["uy"]])
+    assert rel_l2(u, ur) < 1e-9
+    assert rel_l2(np.concatenate([sol_csr.ux, sol_csr.uy]), ur) < 1e-9
+    assert np.abs(sol.stress - ref["stress"]).max() / np.abs(ref["stress"]).max() < 1e-8
+    f, fr = np.concatenate([sol.fx, sol.fy]), np.concatenate([ref["fx"], ref["fy"]])
+    assert np.abs(f - fr).max() / np.abs(fr).max() < 1e-8
+    assert sol.stats["converged"] == 1 and sol.stats["final_residual"] <= 1e-4
+    # given the SAME displacements the device post-processing is bit-identical to the oracle
+    s_dev, sig_dev = solver.stress_soa(mesh, META, ref["ux"], ref["uy"], want_sigma=True, ctx=ctx)
+    s_ref, sig_ref = O.stress(om, META, ref["ux"], ref["uy"], want_sigma=True)
+    assert np.array_equal(s_dev, s_ref) and np.array_equal(sig_dev, sig_ref)
+    # equilibrium: reactions + applied forces sum to ~0
+    assert abs(sol.fx.sum()) / np.abs(sol.fx).max() < 1e-8 and abs(sol.fy.sum()) / np.abs(sol.fx).max() < 1e-8
+
+
+def test_north_star_pcg_mode(ctx):
+    """Jacobi-PCG to 1e-9 relative residual (the benchmark configuration) still lands within the
+    displacement tolerance of a tight solve on a small mesh when asked for a tight residual."""
+    mesh = meshgen.jitter(meshgen.plate(40, 20))
+    ref = O.run(O.Mesh(mesh), META, O.cg_options(), dense=False)
+    ur = np.concatenate([ref["ux"], ref["uy"]])
+    with solver.System(mesh, META, ctx) as S:
+        tight = S.solve(_lib.default_options(rel_tol=1e-13))
+        loose = S.solve(_lib.default_options())                       # rel_tol 1e-9, Jacobi
+        nopre = S.solve(_lib.default_options(precond=0))
+    assert rel_l2(np.concatenate([tight.ux, tight.uy]), ur) < 1e-9
+    assert loose.stats["final_residual"] <= 1e-9 * loose.stats["b_norm"]
+    assert loose.stats["iters"] < tight.stats["iters"]
+    assert rel_l2(np.concatenate([loose.ux, loose.uy]), ur) < 1e-6
+    assert nopre.stats["converged"] == 1
+    port = O.run(O.Mesh(mesh), META, O.cg_options(jacobi=1, rel_tol=1e-9), dense=False)
+    assert abs(int(loose.stats["iters"]) - int(port["stats"]["iters"])) <= max(3, port["stats"]["iters"] // 50)
+
+
+def test_bit_identical_across_runs(ctx):
+    mesh = meshgen.jitter(meshgen.plate(64, 32))
+    outs = []
+    for _ in range(2):
+        with solver.System(mesh, META, ctx) as S:
+            kff = S.export_kff()
+            sol = S.solve(_lib.default_options())
+        outs.append((kff, sol))
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert a.tobytes() == b.tobytes()
+    for k in ("ux", "uy", "fx", "fy", "stress"):
+        assert getattr(outs[0][1], k).tobytes() == getattr(outs[1][1], k).tobytes()
+    assert outs[0][1].stats["iters"] == outs[1][1].stats["iters"]
+
+
+def test_clockwise_mesh_is_negative_definite_but_solves(ctx):
+    g = np.load(GOLDEN / "clockwise_unit.npz")
+    sol = solver.solve_soa(golden_mesh(g), META, ctx, compat())
+    assert sol.stats["negative_definite"] == 1
+    assert rel_l2(np.concatenate([sol.ux, sol.uy]), np.concatenate([g["ux"], g["uy"]])) < 1e-9
+    sol_j = solver.solve_soa(golden_mesh(g), META, ctx, _lib.default_options(rel_tol=1e-13))
+    assert rel_l2(np.concatenate([sol_j.ux, sol_j.uy]), np.concatenate([g["ux"], g["uy"]])) < 1e-9
+
+
+def test_drop_in_run_signature_and_csv(ctx, tmp_path, capsys):
+    """solver::run's signature on AoS nodes/elements, then csv_output, like main.rs:64-69."""
+    from magnetite_b200 import post_processor
+    mesh = meshgen.plate(12, 6)
+    nodes, elements = mesh.to_aos()
+    assert nodes[0].fx is None and nodes[1].ux is None and elements[0].stress is None
+    solver.run(nodes, elements, META)
+    out = capsys.readouterr().out
+    assert "info: building element stiffness matrices..." in out and "info: solve complete" in out
+    assert "info: finished conjugate gradient approximation in" in out
+    ref = O.run(O.Mesh(mesh), META, O.cg_options(), dense=True)
+    u = np.array([[n.ux, n.uy] for n in nodes]); s = np.array([e.stress for e in elements])
+    assert rel_l2(u.ravel(), np.stack([ref["ux"], ref["uy"]], 1).ravel()) < 1e-9
+    assert np.abs(s - ref["stress"]).max() / np.abs(ref["stress"]).max() < 1e-8
+    assert all(n.fx is not None and n.fy is not None for n in nodes)
+    post_processor.csv_output(elements, nodes, str(tmp_path / "nodes.csv"), str(tmp_path / "elements.csv"), quiet=True)
+    rows = (tmp_path / "nodes.csv").read_text().splitlines()
+    assert rows[0] == "x,y,ux,uy" and len(rows) == len(nodes) + 1
+    assert rows[1] == "0,0,0,0" and rows[13].startswith("24,0,3,")
+    erows = (tmp_path / "elements.csv").read_text().splitlines()
+    assert erows[0] == "n0,n1,n2,stress" and erows[1].startswith("0,1,14,")
+    assert solver.compute_element_area(elements[0], nodes) == 2.0
+
+
+def test_error_paths(ctx):
+    mesh = meshgen.plate(6, 3)
+    bad = mesh.copy(); bad.n2[4] = 10_000
+    with pytest.raises(MagnetiteError) as ei:
+        solver.solve_soa(bad, META, ctx)
+    assert ei.value.code == _lib.MAG_ERR_BAD_INDEX and ei.value.kind == "Solver"
+    bc = mesh.copy(); bc.known[3] = 15
+    with pytest.raises(MagnetiteError) as ei:
+        solver.solve_soa(bc, META, ctx)
+    assert ei.value.code == _lib.MAG_ERR_BAD_BC
+    with solver.System(meshgen.plate(30, 15), META, ctx) as S:
+        with pytest.raises(MagnetiteError) as ei:
+            S.solve(_lib.default_options(max_iter=4))
+        assert ei.value.code == _lib.MAG_ERR_NOT_CONVERGED
+        sol = S.solve(_lib.default_options(max_iter=4), allow_not_converged=True)
+        assert sol.stats["iters"] == 4 and sol.stats["converged"] == 0
+        ok = S.solve(_lib.default_options())                  # the context survives an error
+        assert ok.stats["converged"] == 1
+
+
+def test_empty_and_degenerate_inputs(ctx):
+    z = np.zeros(0)
+    empty = MeshSoA(z, z, np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.uint32), z, z, z, z,
+                    np.zeros(0, np.uint8))
+    sol = solver.solve_soa(empty, META, ctx)
+    assert sol.ux.size == 0 and sol.stress.size == 0 and sol.stats["iters"] == 0
+    # nodes but no elements and nothing to solve: everything prescribed
+    m = meshgen.patch_square()
+    allfixed = m.copy(); allfixed.known[:] = 3
+    sol = solver.solve_soa(allfixed, META, ctx)
+    ref = O.run(O.Mesh(allfixed), META, dense=True)
+    assert sol.stats["n_free"] == 0 and np.array_equal(sol.ux, ref["ux"])
+    assert np.array_equal(sol.fx, ref["fx"]) and np.array_equal(sol.stress, ref["stress"])
+    # zero load: b = 0 -> 0 iterations, u = 0 (argmin stops on the initial cost)
+    zero = meshgen.plate(5, 4, ux_right=0.0)
+    sol = solver.solve_soa(zero, META, ctx, compat())
+    assert sol.stats["iters"] == 0 and not sol.ux.any() and not sol.uy.any()
+    # an isolated node that no element references keeps an empty matrix row
+    iso = meshgen.plate(4, 3).copy()
+    iso = MeshSoA(np.append(iso.x, 99.0), np.append(iso.y, 99.0), iso.n0, iso.n1, iso.n2, np.append(iso.ux, 0.0),
+                  np.append(iso.uy, 0.0), np.append(iso.fx, 0.0), np.append(iso.fy, 0.0), np.append(iso.known, 3).astype(np.uint8))
+    sol = solver.solve_soa(iso, META, ctx, compat())
+    ref = O.run(O.Mesh(iso), META, dense=True)
+    assert rel_l2(np.concatenate([sol.ux, sol.uy]), np.concatenate([ref["ux"], ref["uy"]])) < 1e-9
+
+
+def test_device_generated_plate_matches_host_generator(ctx):
+    import ctypes as C
+    lib = _lib.load()
+    dm = C.c_void_p()
+    _lib.check(lib.mag_devmesh_plate(ctx.handle, 37, 11, 2.0, 3.0, C.byref(dm)), "devmesh")
+    view = _lib.MagMesh()
+    _lib.check(lib.mag_devmesh_view(dm, C.byref(view)), "view")
+    assert view.on_device == 1 and view.n_elems == 2 * 37 * 11
+    mat = _lib.MagMaterial(META.youngs_modulus, META.poisson_ratio, META.part_thickness)
+    opt = _lib.default_options(rel_tol=1e-12)
+    sysh = C.c_void_p(); st = _lib.MagStats()
+    _lib.check(lib.mag_assemble(ctx.handle, C.byref(view), C.byref(mat), C.byref(opt), C.byref(sysh), C.byref(st)), "assemble")
+    host = meshgen.plate(37, 11)
+    with solver.System(host, META, ctx) as S:
+        ref_kff = S.export_kff()
+        n_free, nnz = S.n_free, S.nnz
+    assert (st.n_free, st.nnz) == (n_free, nnz)
+    rowptr = np.empty(n_free + 1, np.int64); col = np.empty(nnz, np.int32); val = np.empty(nnz); rhs = np.empty(n_free)
+    _lib.check(lib.mag_system_export_kff(sysh, _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), _lib.ptr(rhs), None), "export")
+    assert np.array_equal(rowptr, ref_kff[0]) and np.array_equal(col, ref_kff[1])
+    assert np.array_equal(val, ref_kff[2]) and np.array_equal(rhs, ref_kff[3])
+    lib.mag_system_free(sysh)
+    lib.mag_devmesh_free(dm)
+
+
+def test_full_size_properties_1m_triangles(ctx):
+    """BASELINE config 3 (1000x500 cells, 1 M triangles): size-independent properties instead of a
+    full oracle run — equilibrium, uniform-strain sanity, pattern counts, determinism of K_ff."""
+    mesh = meshgen.plate(1000, 500)
+    with solver.System(mesh, META, ctx) as S:
+        assert S.n_free == 2 * 501_501 - 2 * 501 - 501
+        rp, col, val, rhs, fmap = S.export_kff()
+        assert (np.diff(rp) > 0).all() and (val != 0.0).all()
+        rows = np.repeat(np.arange(S.n_free), np.diff(rp))
+        # symmetric pattern, ascending columns
+        assert ((col[1:] > col[:-1]) | (rows[1:] != rows[:-1])).all()
+        import scipy.sparse as sp
+        A = sp.csr_matrix((val, col, rp), shape=(S.n_free, S.n_free))
+        assert abs(A - A.T).max() / abs(A).max() < 1e-12
+        sol = S.solve(_lib.default_options())
+        assert sol.stats["converged"] == 1
+        # true residual of the returned solution
+        xfree = np.empty(S.n_free)
+        u = np.stack([sol.ux, sol.uy], 1).ravel()
+        xfree[fmap[fmap >= 0]] = u[fmap >= 0]
+        assert np.linalg.norm(A @ xfree - rhs) / np.linalg.norm(rhs) < 5e-9
+    assert abs(sol.fx.sum()) / np.abs(sol.fx).max() < 1e-6
+    assert sol.ux.min() >= -1e-9 and sol.ux.max() <= 3.0 + 1e-9
+    mid = np.abs(sol.stress[len(sol.stress) // 2])
+    assert 0.5 < mid / (69e9 * 3.0 / 2000.0) < 1.5            # ~ E * strain in the middle of the plate
