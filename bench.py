@@ -170,14 +170,30 @@ def run_ours(args):
     from magnetite_b200 import _lib, meshgen
     from magnetite_b200.solver import _material
 
+    from magnetite_b200 import dist as mdist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        raise SystemExit("multi-GPU bench: see bench_dist in a later commit")  # replaced below when dist lands
     torch.cuda.set_device(local_rank)
     lib = _lib.load()
     ctx = _lib.Context(local_rank)
+    tdist = None
+    if world > 1:
+        import torch.distributed as tdist
+        mdist.init_process_group("nccl")
+        mdist.init_comm(ctx)          # the library's own NCCL communicator (allreduce in the CG graph)
+
+    def barrier():
+        if tdist is not None:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if tdist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return float(t.item())
     stream = torch.cuda.Stream()
     meta = meshgen.EXAMPLE_MATERIAL
     mat = _material(meta)
@@ -204,8 +220,8 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         device_step()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stats = []
     with torch.cuda.stream(stream):
@@ -213,15 +229,15 @@ def run_ours(args):
         for _ in range(args.steps):
             stats.append(device_step())
         ev1.record(stream)
-    torch.cuda.synchronize()
-    ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
     value = E / (ms_step * 1e-3) / 1e6
     last = stats[-1]
     launches = int(sum(s.kernel_launches for s in stats))
-    ms_asm = statistics.mean(s.ms_elem + s.ms_sort + s.ms_reduce + s.ms_bc for s in stats)
-    ms_solve = statistics.mean(s.ms_solve for s in stats)
+    ms_asm = max_over_ranks(statistics.mean(s.ms_elem + s.ms_sort + s.ms_reduce + s.ms_bc for s in stats))
+    ms_solve = max_over_ranks(statistics.mean(s.ms_solve for s in stats))
 
     # ---- roofline of the dominant kernel: the PCG SpMV, timed live ---------------------
     sysh = C.c_void_p()
@@ -230,11 +246,12 @@ def run_ours(args):
                "mag_assemble")
     ms_spmv, nbytes = C.c_float(), C.c_uint64()
     _lib.check(lib.mag_system_spmv_bench(sysh, 2, args.spmv_reps, C.byref(ms_spmv), C.byref(nbytes)), "spmv_bench")
+    n_local_rows = (int(st.spmv_bytes) - 12 * int(st.nnz) - 4) // 20
     lib.mag_system_free(sysh)
     peak, peak_src = measured_peak()
     csr_bytes = int(last.spmv_bytes)
-    achieved = nbytes.value / (ms_spmv.value * 1e-3) / 1e9
-    iter_bytes = nbytes.value + 88 * int(last.n_free)
+    achieved = nbytes.value / (ms_spmv.value * 1e-3) / 1e9         # this rank's block, this rank's GPU
+    iter_bytes = nbytes.value + 88 * n_local_rows
     ms_iter = ms_solve / max(int(last.iters), 1)
     roofline = {"bound": "hbm", "kernel": "pcg_spmv_kernel (SELL-32 SpMV + fused p.q)", "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
@@ -246,6 +263,7 @@ def run_ours(args):
 
     # ---- end to end: pinned host buffers through mag_solve ----------------------------------
     e2e = None
+    barrier()
     if not args.no_e2e:
         host = meshgen.plate(nx, ny)
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -268,22 +286,22 @@ def run_ours(args):
             return s
 
         host_step()
-        torch.cuda.synchronize()
+        barrier()
         e_steps = max(1, min(args.steps, 2))
         with torch.cuda.stream(stream):
             ev0.record(stream)
             for _ in range(e_steps):
                 host_step()
             ev1.record(stream)
-        torch.cuda.synchronize()
-        ms_e2e = ev0.elapsed_time(ev1) / e_steps
+        barrier()
+        ms_e2e = max_over_ranks(ev0.elapsed_time(ev1)) / e_steps
         e2e = {"value": E / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e_steps,
                "checksum_ux_max": float(out_h["ux"].max())}
 
     # ---- CPU baseline beside it ----------------------------------------------------------------
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         v, dt, cst = cpu_sample(args.ref_nx, args.ref_ny)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"plate {args.ref_nx}x{args.ref_ny} cells ({2 * args.ref_nx * args.ref_ny} triangles) solved "
@@ -292,11 +310,19 @@ def run_ours(args):
                          f"{nx}x{ny} workload costs the CPU ~{nx / args.ref_nx:.0f}x more",
                "seconds": dt, "host_cores_available": os.cpu_count()}
 
+    if rank != 0:
+        barrier()
+        lib.mag_devmesh_free(dm)
+        ctx.close()
+        tdist.destroy_process_group()
+        return
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(nx, ny), "parallelism": "1 GPU",
+        "config": {"workload": workload_name(nx, ny),
+                   "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: contiguous row blocks, P2P halo stores fused "
+                                  f"into the CG update kernel, NCCL allreduce for the dot products",
                    "l2": "inputs larger than L2 (K_ff + vectors >> 126 MB), no flush needed",
                    "solver": "Jacobi-PCG, rel_tol 1e-9, SELL-32 SpMV", "n_free": int(last.n_free),
                    "nnz": int(last.nnz), "nnz_structural": int(last.nnz_structural)},
@@ -309,8 +335,12 @@ def run_ours(args):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
+    if world > 1:
+        barrier()
     lib.mag_devmesh_free(dm)
     ctx.close()
+    if tdist is not None:
+        tdist.destroy_process_group()
 
 
 def main():

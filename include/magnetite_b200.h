@@ -177,10 +177,20 @@ int mag_comm_init(mag_ctx *ctx, int rank, int nranks, const void *id128);
 int mag_comm_rank(const mag_ctx *ctx, int *rank, int *nranks);
 /* node range [lo,hi) owned by `rank` of `nranks` for a mesh of n_nodes */
 int mag_partition_nodes(uint64_t n_nodes, int nranks, int rank, uint64_t *lo, uint64_t *hi);
+/* halo plan of `rank` (host logic, no device needed): given every rank's reduced-row
+ * boundaries row_lo[0..nranks] and the column extent [ext_lo[r], ext_hi[r]) its rows touch,
+ * lists the index ranges [seg_lo,seg_hi) of `rank`'s own rows that rank seg_dst reads as halo. */
+int mag_halo_plan(int nranks, int rank, const uint32_t *row_lo, const uint32_t *ext_lo,
+                  const uint32_t *ext_hi, uint32_t *seg_lo, uint32_t *seg_hi, int32_t *seg_dst,
+                  int32_t capacity, int32_t *n_segs);
 
 /* ---- debug entry points used by the GPU unit tests ----------------------- */
 int mag_debug_sort_pairs(mag_ctx *ctx, uint64_t *keys, uint32_t *payload, uint64_t n, int key_bits);
 int mag_debug_exclusive_scan(mag_ctx *ctx, const uint32_t *in, uint32_t *out /*n+1*/, uint64_t n);
+/* nranks-way row-block solve emulated on ONE GPU: the same partitioning, kernels and halo
+ * stores as the multi-process path, with the allreduce replaced by a kernel. */
+int mag_debug_virtual_solve(mag_ctx *ctx, const mag_mesh *mesh, const mag_material *mat,
+                            const mag_options *opt, int nranks, mag_result *out, mag_stats *stats);
 
 #ifdef __cplusplus
 }

@@ -97,8 +97,11 @@ _SIGNATURES = {
     "mag_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "mag_comm_rank": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mag_partition_nodes": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "mag_halo_plan": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.POINTER(C.c_int32)]),
     "mag_debug_sort_pairs": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_int]),
     "mag_debug_exclusive_scan": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
+    "mag_debug_virtual_solve": (C.c_int, [_vp, C.POINTER(MagMesh), C.POINTER(MagMaterial), C.POINTER(MagOptions),
+                                          C.c_int, C.POINTER(MagResult), C.POINTER(MagStats)]),
 }
 
 _lib = None

@@ -2,9 +2,11 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -49,7 +51,29 @@ constexpr int kWarp = 32;
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
-struct Comm;   // dist.cuh
+struct Comm;   // comm.cuh
+
+// Device heap of a context: first-fit free list with coalescing over a few large
+// cudaMalloc slabs that are kept for the life of the context.  A repeated
+// solve issues the same allocation sequence and therefore lands on the same
+// addresses without ever touching the driver allocator again (the CUDA
+// stream-ordered pool re-created multi-GB blocks between steps, which cost
+// more than the whole assembly).  Blocks are recycled at host time; that is
+// safe because every call runs on one stream and every entry point is blocking.
+class DeviceHeap {
+public:
+    void *alloc(size_t bytes);
+    void release(void *p);
+    void destroy();
+    size_t reserved() const { return reserved_; }
+private:
+    struct Slab { char *base; size_t size; };
+    std::vector<Slab> slabs_;
+    std::map<char *, size_t> free_;     // start -> size, coalesced within a slab
+    std::map<char *, size_t> used_;
+    size_t reserved_ = 0;
+    void add_slab(size_t at_least);
+};
 
 }  // namespace mag
 
@@ -59,7 +83,7 @@ struct mag_ctx {
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;      // stream of the current call (own or caller's)
-    cudaMemPool_t pool = nullptr;
+    mag::DeviceHeap heap;
     uint64_t launches = 0;              // kernels launched by the current call
     mag::Comm *comm = nullptr;
     // pinned host scratch for scalar read-backs
@@ -68,8 +92,74 @@ struct mag_ctx {
 
 namespace mag {
 
-// Stream-ordered device buffer (cudaMallocAsync on the context's pool: repeated
-// solves reuse the same physical memory without touching the OS allocator).
+inline void DeviceHeap::add_slab(size_t at_least) {
+    size_t want = std::max<size_t>(at_least, std::max<size_t>(reserved_ / 2, (size_t)256 << 20));
+    want = (want + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    char *base = nullptr;
+    cudaError_t e = cudaMalloc((void **)&base, want);
+    if (e != cudaSuccess && want > at_least) {      // growth headroom refused: take the bare minimum
+        cudaGetLastError();
+        want = (at_least + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+        e = cudaMalloc((void **)&base, want);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fail(MAG_ERR_OOM, "device heap: cudaMalloc of %zu MiB failed (%zu MiB already reserved): %s",
+             want >> 20, reserved_ >> 20, cudaGetErrorString(e));
+    }
+    slabs_.push_back({base, want});
+    free_[base] = want;
+    reserved_ += want;
+}
+
+inline void *DeviceHeap::alloc(size_t bytes) {
+    bytes = (bytes + 511) & ~(size_t)511;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        for (auto it = free_.begin(); it != free_.end(); ++it) {
+            if (it->second >= bytes) {
+                char *p = it->first;
+                const size_t rest = it->second - bytes;
+                free_.erase(it);
+                if (rest) free_[p + bytes] = rest;
+                used_[p] = bytes;
+                return p;
+            }
+        }
+        add_slab(bytes);
+    }
+    fail(MAG_ERR_OOM, "device heap: allocation of %zu bytes failed", bytes);
+}
+
+inline void DeviceHeap::release(void *ptr) {
+    char *p = static_cast<char *>(ptr);
+    auto u = used_.find(p);
+    if (u == used_.end()) return;
+    size_t size = u->second;
+    used_.erase(u);
+    // blocks never straddle slabs, and neighbours in different slabs must not merge
+    const Slab *slab = nullptr;
+    for (const Slab &s : slabs_) if (p >= s.base && p < s.base + s.size) { slab = &s; break; }
+    auto next = free_.lower_bound(p);
+    if (next != free_.end() && next->first == p + size && slab && next->first < slab->base + slab->size) {
+        size += next->second;
+        next = free_.erase(next);
+    }
+    if (next != free_.begin()) {
+        auto prev = std::prev(next);
+        if (prev->first + prev->second == p && slab && prev->first >= slab->base) {
+            prev->second += size;
+            return;
+        }
+    }
+    free_[p] = size;
+}
+
+inline void DeviceHeap::destroy() {
+    for (const Slab &s : slabs_) cudaFree(s.base);
+    slabs_.clear(); free_.clear(); used_.clear(); reserved_ = 0;
+}
+
+// Device buffer carved from the context's heap.
 template <class T>
 struct DevBuf {
     T *p = nullptr;
@@ -87,12 +177,11 @@ struct DevBuf {
     void alloc(mag_ctx *c, size_t count) {
         release();
         ctx = c; n = count;
-        size_t bytes = (count ? count : 1) * sizeof(T);
-        MAG_CUDA(cudaMallocAsync((void **)&p, bytes, c->stream));
+        p = static_cast<T *>(c->heap.alloc((count ? count : 1) * sizeof(T)));
     }
     void zero() { if (p) MAG_CUDA(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), ctx->stream)); }
     void release() {
-        if (p) { cudaFreeAsync(p, ctx->stream); p = nullptr; n = 0; }
+        if (p) { ctx->heap.release(p); p = nullptr; n = 0; }
     }
     ~DevBuf() { release(); }
     size_t bytes() const { return n * sizeof(T); }

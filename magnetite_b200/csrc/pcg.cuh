@@ -1,17 +1,28 @@
 // pcg.cuh — conjugate gradients on the device (replaces argmin's
-// ConjugateGradient + Executor at reference src/solver.rs:141-157).
+// ConjugateGradient + Executor at reference src/solver.rs:141-157), written so
+// the same kernels run on one GPU and on a row-block partition over several.
 //
-// Three kernels per iteration, all scalars (alpha, beta, residual, iteration
-// count, stop flag) live in device memory, so an iteration needs no host round
-// trip; `check_every` iterations are captured in one CUDA graph and the host
-// only polls the stop flag between graph launches.  Once the flag is set every
+// Three kernels per iteration; alpha, beta, the residual, the iteration count
+// and the stop flag live in device memory, so an iteration needs no host round
+// trip.  `check_every` iterations are captured in one CUDA graph and the host
+// only polls the stop flag between graph launches; once the flag is set every
 // kernel returns immediately, so the result is the iterate at the exact
 // stopping iteration regardless of the chunk size.
 //
-//   A: q = K p            and  pq  = p.q            (SELL SpMV + fused dot)
-//   B: alpha = rz/pq;  x += alpha p;  r -= alpha q;  rz' = r.(Dinv r);  rr = r.r
-//      last CTA: iteration count, stop test
-//   C: beta = rz'/rz;  p = Dinv r + beta p
+//   A: q = K p  and  pq = p.q                      (SELL SpMV + fused dot)
+//      [multi-GPU: allreduce pq]
+//   B: alpha = rz/pq;  x += alpha p;  r -= alpha q;  {rz', rr} = {r.Dinv r, r.r}
+//      r is stored by GLOBAL reduced row; boundary entries are also stored
+//      straight into the neighbouring GPUs' copies over NVLink (peer pointers),
+//      so the halo exchange costs no extra launch and no extra synchronisation:
+//      the allreduce that follows orders it.
+//      [multi-GPU: allreduce {rz', rr}]
+//   C: iteration count + stop test; beta = rz'/rz;  p = Dinv r + beta p over the
+//      owned rows AND the halo rows (each GPU updates its own copy of the halo
+//      of p from the halo of r it was sent).
+//
+// Vectors p, r, Dinv are indexed by global reduced row (owned block + halo
+// valid); x, q by local row.
 //
 // compat mode (reference semantics): no preconditioner, x0 = 0, stop when the
 // cost (||r||_2, or r.r) is <= 1e-4 absolute or after 1e7 iterations
@@ -24,27 +35,30 @@
 namespace mag {
 
 struct PcgScalars {
-    double rz[2];        // r.z of the current / next iteration (index = iteration parity)
+    double pair[2][2];   // pair[parity] = {r.z, r.r} entering an iteration of that parity
     double pq;
-    double rr;           // r.r after the last completed iteration
-    double thr2;         // stop when rr <= thr2
-    double first_pq;     // sign tells negative-definite systems
+    double thr2;         // stop when r.r <= thr2
+    double first_pq;     // its sign tells negative-definite systems
     unsigned long long iter, max_iter;
     int stop;            // 1: converged, 2: max_iter, 3: breakdown
     unsigned ticket_a, ticket_b;
     int pad;
 };
 
-struct PcgWork {
-    uint32_t n = 0;              // local rows
-    uint32_t row_lo = 0;         // global index of local row 0
-    DevBuf<double> x, r, q, dinv;
-    DevBuf<double> p_store;      // global-indexed direction vector (owned part + halo)
-    double *p = nullptr;         // = p_store.p (index by global reduced row)
-    DevBuf<double> partials;     // 2 * grid
-    DevBuf<PcgScalars> scal;
-    unsigned grid_vec = 1, grid_spmv = 1;
+constexpr int kMaxPush = 16;
+// Index ranges [lo,hi) of MY rows (global reduced index) that other ranks read as
+// halo, and the base pointer of the destination rank's global-indexed arrays.
+struct PushSegs {
+    int n = 0;
+    uint32_t lo[kMaxPush], hi[kMaxPush];
+    double *r_dst[kMaxPush];
+    double *dinv_dst[kMaxPush];
 };
+
+__device__ __forceinline__ void push_value(const PushSegs &ps, uint32_t gi, double v, bool dinv) {
+    for (int s = 0; s < ps.n; ++s)
+        if (gi >= ps.lo[s] && gi < ps.hi[s]) (dinv ? ps.dinv_dst[s] : ps.r_dst[s])[gi] = v;
+}
 
 __global__ void __launch_bounds__(256, 6)
 pcg_spmv_kernel(const uint32_t *__restrict__ slice_off, const int32_t *__restrict__ scol,
@@ -54,10 +68,7 @@ pcg_spmv_kernel(const uint32_t *__restrict__ slice_off, const int32_t *__restric
     if (sc->stop) return;
     double v[1] = {sell_rows<true>(slice_off, scol, sval, p, q, n_rows, n_slices, row_lo)};
     double tot[1];
-    if (grid_sum_256<1>(v, partials, &sc->ticket_a, tot)) {
-        sc->pq = tot[0];
-        if (sc->iter == 0) sc->first_pq = tot[0];
-    }
+    if (grid_sum_256<1>(v, partials, &sc->ticket_a, tot)) sc->pq = tot[0];
 }
 
 // same, scalar CSR (format comparison)
@@ -77,76 +88,118 @@ pcg_spmv_csr_kernel(const uint32_t *__restrict__ rowptr, const int32_t *__restri
     }
     double v[1] = {dot};
     double tot[1];
-    if (grid_sum_256<1>(v, partials, &sc->ticket_a, tot)) {
-        sc->pq = tot[0];
-        if (sc->iter == 0) sc->first_pq = tot[0];
-    }
+    if (grid_sum_256<1>(v, partials, &sc->ticket_a, tot)) sc->pq = tot[0];
 }
 
 __global__ void __launch_bounds__(256)
 pcg_update_xr_kernel(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
                      const double *__restrict__ q, const double *__restrict__ dinv, uint32_t n,
-                     uint32_t row_lo, int parity, double *__restrict__ partials,
+                     uint32_t row_lo, int parity, PushSegs push, double *__restrict__ partials,
                      PcgScalars *__restrict__ sc) {
     if (sc->stop) return;
-    const double pq = sc->pq;
-    const double alpha = sc->rz[parity] / pq;
+    const double alpha = sc->pair[parity][0] / sc->pq;
     double v[2] = {0.0, 0.0};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const double pi = p[row_lo + i], qi = q[i];
-        const double xi = fma(alpha, pi, x[i]);
-        const double ri = fma(-alpha, qi, r[i]);
+        const uint32_t gi = row_lo + i;
+        const double xi = fma(alpha, p[gi], x[i]);
+        const double ri = fma(-alpha, q[i], r[gi]);
         x[i] = xi;
-        r[i] = ri;
-        v[0] = fma(ri * dinv[i], ri, v[0]);   // r.z with z = Dinv r
+        r[gi] = ri;
+        if (push.n) push_value(push, gi, ri, false);
+        v[0] = fma(ri * dinv[gi], ri, v[0]);   // r.z with z = Dinv r
         v[1] = fma(ri, ri, v[1]);
     }
     double tot[2];
     if (grid_sum_256<2>(v, partials, &sc->ticket_b, tot)) {
-        sc->rz[parity ^ 1] = tot[0];
-        sc->rr = tot[1];
-        const unsigned long long it = sc->iter + 1;
-        sc->iter = it;
-        if (!(pq != 0.0) || !(tot[1] == tot[1])) sc->stop = 3;      // breakdown / NaN
-        else if (tot[1] <= sc->thr2) sc->stop = 1;
-        else if (it >= sc->max_iter) sc->stop = 2;
+        sc->pair[parity ^ 1][0] = tot[0];
+        sc->pair[parity ^ 1][1] = tot[1];
     }
 }
 
+// Rows [ext_lo, ext_hi) = owned block plus halo.
 __global__ void __launch_bounds__(256)
 pcg_update_p_kernel(double *__restrict__ p, const double *__restrict__ r,
-                    const double *__restrict__ dinv, uint32_t n, uint32_t row_lo, int parity,
-                    const PcgScalars *__restrict__ sc) {
+                    const double *__restrict__ dinv, uint32_t ext_lo, uint32_t ext_hi, int parity,
+                    PcgScalars *__restrict__ sc) {
     if (sc->stop) return;
-    const double beta = sc->rz[parity ^ 1] / sc->rz[parity];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        p[row_lo + i] = fma(beta, p[row_lo + i], r[i] * dinv[i]);
+    const double rz_new = sc->pair[parity ^ 1][0], rr = sc->pair[parity ^ 1][1];
+    const double rz_old = sc->pair[parity][0], pq = sc->pq;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long it = sc->iter + 1;
+        if (sc->iter == 0) sc->first_pq = pq;
+        sc->iter = it;
+        if (!(pq != 0.0) || !(rr == rr)) sc->stop = 3;          // breakdown / NaN
+        else if (rr <= sc->thr2) sc->stop = 1;
+        else if (it >= sc->max_iter) sc->stop = 2;
+    }
+    const double beta = rz_new / rz_old;
+    const uint32_t n = ext_hi - ext_lo;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t gi = ext_lo + i;
+        p[gi] = fma(beta, p[gi], r[gi] * dinv[gi]);
+    }
 }
 
-// x = 0, r = b, dinv from the diagonal, p = Dinv r, rz = r.z, rr = r.r
+// x = 0, r = b, Dinv from the diagonal (both pushed to the neighbours), {r.z, r.r}
 __global__ void __launch_bounds__(256)
-pcg_init_kernel(double *__restrict__ x, double *__restrict__ r, double *__restrict__ p,
-                double *__restrict__ dinv, const double *__restrict__ b,
-                const double *__restrict__ diag, int jacobi, uint32_t n, uint32_t row_lo,
-                double *__restrict__ partials, PcgScalars *__restrict__ sc) {
+pcg_init_kernel(double *__restrict__ x, double *__restrict__ r, double *__restrict__ dinv,
+                const double *__restrict__ b, const double *__restrict__ diag, int jacobi, uint32_t n,
+                uint32_t row_lo, PushSegs push, double *__restrict__ partials,
+                PcgScalars *__restrict__ sc) {
     double v[2] = {0.0, 0.0};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t gi = row_lo + i;
         const double d = diag[i];
         const double di = (jacobi && d != 0.0) ? 1.0 / d : 1.0;
         const double bi = b[i];
-        dinv[i] = di;
+        dinv[gi] = di;
         x[i] = 0.0;
-        r[i] = bi;
-        const double z = bi * di;
-        p[row_lo + i] = z;
-        v[0] = fma(bi, z, v[0]);
+        r[gi] = bi;
+        if (push.n) { push_value(push, gi, bi, false); push_value(push, gi, di, true); }
+        v[0] = fma(bi * di, bi, v[0]);
         v[1] = fma(bi, bi, v[1]);
     }
     double tot[2];
     if (grid_sum_256<2>(v, partials, &sc->ticket_b, tot)) {
-        sc->rz[0] = tot[0];
-        sc->rr = tot[1];
+        sc->pair[0][0] = tot[0];
+        sc->pair[0][1] = tot[1];
     }
+}
+
+// p = Dinv r over owned + halo rows (after the neighbours' pushes are visible)
+__global__ void pcg_init_p_kernel(double *__restrict__ p, const double *__restrict__ r,
+                                  const double *__restrict__ dinv, uint32_t ext_lo, uint32_t ext_hi) {
+    const uint32_t n = ext_hi - ext_lo;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        p[ext_lo + i] = r[ext_lo + i] * dinv[ext_lo + i];
+}
+
+// Single-process emulation of an allreduce(sum) over R virtual ranks: sums `count`
+// doubles at byte offset `off` of every rank's PcgScalars in rank order and
+// writes the result back to all of them.  (Tests only.)
+struct ScalPtrs { int n; PcgScalars *p[16]; };
+__global__ void emulated_allreduce_kernel(ScalPtrs sp, int off_doubles, int count) {
+    const int j = threadIdx.x;
+    if (j >= count) return;
+    double s = 0.0;
+    for (int r = 0; r < sp.n; ++r) s += reinterpret_cast<double *>(sp.p[r])[off_doubles + j];
+    for (int r = 0; r < sp.n; ++r) reinterpret_cast<double *>(sp.p[r])[off_doubles + j] = s;
+}
+
+// [min, max] of the column indices of a CSR block (halo extent of a rank)
+__global__ void col_range_kernel(const int32_t *__restrict__ col, size_t nnz, int *__restrict__ mn,
+                                 int *__restrict__ mx) {
+    int lo = 0x7fffffff, hi = -1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = col[i];
+        lo = min(lo, c); hi = max(hi, c);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(mn, lo); atomicMax(mx, hi); }
 }
 
 }  // namespace mag

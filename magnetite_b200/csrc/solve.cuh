@@ -1,0 +1,421 @@
+// solve.cuh — host orchestration of the PCG solve and the post-processing, for
+// one rank per process (production; NCCL + CUDA IPC between processes) or for
+// several "virtual ranks" inside one process (single-GPU emulation used by the
+// tests: same partition, same kernels, same halo stores, allreduce emulated by a
+// tiny kernel).
+#pragma once
+#include <cmath>
+
+#include "system.cuh"
+
+namespace mag {
+
+struct RankState {
+    mag_system *S = nullptr;
+    uint32_t n = 0;                  // owned rows
+    DevBuf<double> x, q;             // local
+    DevBuf<double> p_ext;            // global-indexed
+    DevBuf<double> own_slab;         // r|dinv when the system has no shared slab (single rank)
+    double *r_ext = nullptr, *dinv_ext = nullptr;
+    DevBuf<double> partials;
+    DevBuf<PcgScalars> scal;
+    unsigned grid_vec = 1, grid_spmv = 1, grid_ext = 1;
+};
+
+inline size_t ext_len(const mag_system *S) { return (size_t)S->n_free + 32; }
+
+// Allocates the slab other ranks store into (plain cudaMalloc so it can be exported).
+static void ensure_shared_slab(mag_system *S) {
+    if (S->shared_slab) return;
+    MAG_CUDA(cudaMalloc((void **)&S->shared_slab, 2 * ext_len(S) * sizeof(double)));
+}
+
+// Which of MY rows do the other ranks need?  Pure host logic (also exported as
+// mag_halo_plan for the CPU tests): rank r reads [ext_lo[r], row_lo[r]) and
+// [row_lo[r+1], ext_hi[r]) from whoever owns those rows; the part inside my block
+// [row_lo[me], row_lo[me+1]) is what I store into r's buffers.
+struct HaloSeg { uint32_t lo, hi; int dst; };
+static std::vector<HaloSeg> halo_plan(int nranks, int me, const uint32_t *row_lo, const uint32_t *ext_lo,
+                                      const uint32_t *ext_hi) {
+    std::vector<HaloSeg> segs;
+    for (int r = 0; r < nranks; ++r) {
+        if (r == me) continue;
+        const uint32_t need[2][2] = {{ext_lo[r], row_lo[r]}, {row_lo[r + 1], ext_hi[r]}};
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t lo = std::max(need[k][0], row_lo[me]), hi = std::min(need[k][1], row_lo[me + 1]);
+            if (lo < hi) segs.push_back({lo, hi, r});
+        }
+    }
+    return segs;
+}
+
+// `peer_slab[r]` is rank r's shared slab as seen from this process.
+static void build_push_segments(mag_system *S, const std::vector<uint32_t> &ext_lo,
+                                const std::vector<uint32_t> &ext_hi,
+                                const std::vector<double *> &peer_slab) {
+    PushSegs &ps = S->push;
+    ps.n = 0;
+    const size_t L = ext_len(S);
+    for (const HaloSeg &g : halo_plan(S->nranks, S->rank, S->all_row_lo.data(), ext_lo.data(), ext_hi.data())) {
+        if (ps.n == kMaxPush) fail(MAG_ERR_BAD_ARG, "halo pattern needs more than %d push segments", kMaxPush);
+        if (!peer_slab[g.dst]) fail(MAG_ERR_BAD_ARG, "no mapping of rank %d's halo buffer", g.dst);
+        ps.lo[ps.n] = g.lo; ps.hi[ps.n] = g.hi;
+        ps.r_dst[ps.n] = peer_slab[g.dst];
+        ps.dinv_dst[ps.n] = peer_slab[g.dst] + L;
+        ++ps.n;
+    }
+    S->push_ready = true;
+}
+
+// Production: exchange halo extents and IPC handles with the other processes.
+static void setup_halo_ipc(mag_ctx *ctx, mag_system *S) {
+    if (S->push_ready) return;
+    const int R = S->nranks;
+    ensure_shared_slab(S);
+    std::vector<uint32_t> mine = {S->ext_lo, S->ext_hi}, all(2 * (size_t)R);
+    allgather_u32(ctx, mine.data(), 2, all.data());
+    std::vector<uint32_t> elo(R), ehi(R);
+    for (int r = 0; r < R; ++r) { elo[r] = all[2 * r]; ehi[r] = all[2 * r + 1]; }
+    cudaIpcMemHandle_t h;
+    MAG_CUDA(cudaIpcGetMemHandle(&h, S->shared_slab));
+    std::vector<cudaIpcMemHandle_t> hs(R);
+    allgather_bytes(ctx, &h, sizeof h, hs.data());
+    std::vector<double *> peer(R, nullptr);
+    for (int r = 0; r < R; ++r) {
+        if (r == S->rank) { peer[r] = S->shared_slab; continue; }
+        // open only the ranks I actually store into
+        bool needed = false;
+        for (const HaloSeg &g : halo_plan(R, S->rank, S->all_row_lo.data(), elo.data(), ehi.data()))
+            needed = needed || g.dst == r;
+        if (!needed) continue;
+        void *p = nullptr;
+        MAG_CUDA(cudaIpcOpenMemHandle(&p, hs[r], cudaIpcMemLazyEnablePeerAccess));
+        S->ipc_opened.push_back(p);
+        peer[r] = static_cast<double *>(p);
+    }
+    build_push_segments(S, elo, ehi, peer);
+}
+
+static void rank_alloc(mag_ctx *ctx, RankState &W, mag_system *S) {
+    W.S = S;
+    W.n = S->Kff.n_rows;
+    W.x.alloc(ctx, W.n); W.q.alloc(ctx, W.n);
+    W.p_ext.alloc(ctx, ext_len(S));
+    W.p_ext.zero();
+    if (S->shared_slab) {
+        W.r_ext = S->shared_slab;
+    } else {
+        W.own_slab.alloc(ctx, 2 * ext_len(S));
+        W.r_ext = W.own_slab.p;
+    }
+    W.dinv_ext = W.r_ext + ext_len(S);
+    const unsigned cap = (unsigned)ctx->sm_count * 8u;
+    W.grid_vec = std::max(1u, std::min(cdiv(W.n, 256), cap));
+    W.grid_ext = std::max(1u, std::min(cdiv(S->ext_hi - S->ext_lo, 256), cap));
+    W.grid_spmv = sell_grid(ctx, S->sell.n_slices);
+    W.partials.alloc(ctx, 2 * (size_t)std::max(cap, W.grid_spmv));
+    W.scal.alloc(ctx, 1);
+    W.scal.zero();
+}
+
+// Sum over ranks of `count` doubles at `field` inside PcgScalars.
+static void reduce_scalars(mag_ctx *ctx, std::vector<RankState> &ranks, size_t off_doubles, int count) {
+    if (ranks.size() > 1) {          // virtual ranks in one process
+        ScalPtrs sp;
+        sp.n = (int)ranks.size();
+        for (int r = 0; r < sp.n; ++r) sp.p[r] = ranks[r].scal.p;
+        MAG_LAUNCH(ctx, emulated_allreduce_kernel, 1, 32, 0, sp, (int)off_doubles, count);
+    } else {
+        allreduce_sum(ctx, reinterpret_cast<double *>(ranks[0].scal.p) + off_doubles, count);
+    }
+}
+constexpr size_t kOffPair0 = offsetof(PcgScalars, pair) / sizeof(double);
+constexpr size_t kOffPq = offsetof(PcgScalars, pq) / sizeof(double);
+
+static void enqueue_iteration(mag_ctx *ctx, std::vector<RankState> &ranks, int parity, int format) {
+    for (RankState &W : ranks) {
+        const SellMatrix &L = W.S->sell;
+        const CsrMatrix &A = W.S->Kff;
+        if (!W.n) continue;
+        if (format == 1)
+            MAG_LAUNCH(ctx, pcg_spmv_csr_kernel, W.grid_vec, 256, 0, (const uint32_t *)A.rowptr.p,
+                       (const int32_t *)A.col.p, (const double *)A.val.p, (const double *)W.p_ext.p, W.q.p,
+                       W.n, A.row_lo, W.partials.p, W.scal.p);
+        else
+            MAG_LAUNCH(ctx, pcg_spmv_kernel, W.grid_spmv, 256, 0, (const uint32_t *)L.slice_off.p,
+                       (const int32_t *)L.col.p, (const double *)L.val.p, (const double *)W.p_ext.p, W.q.p,
+                       W.n, L.n_slices, L.row_lo, W.partials.p, W.scal.p);
+    }
+    reduce_scalars(ctx, ranks, kOffPq, 1);
+    for (RankState &W : ranks)
+        if (W.n)
+            MAG_LAUNCH(ctx, pcg_update_xr_kernel, W.grid_vec, 256, 0, W.x.p, W.r_ext, (const double *)W.p_ext.p,
+                       (const double *)W.q.p, (const double *)W.dinv_ext, W.n, W.S->row_lo, parity, W.S->push,
+                       W.partials.p, W.scal.p);
+    reduce_scalars(ctx, ranks, kOffPair0 + 2 * (size_t)(parity ^ 1), 2);
+    for (RankState &W : ranks)
+        MAG_LAUNCH(ctx, pcg_update_p_kernel, W.grid_ext, 256, 0, W.p_ext.p, (const double *)W.r_ext,
+                   (const double *)W.dinv_ext, W.S->ext_lo, W.S->ext_hi, parity, W.scal.p);
+}
+
+struct SolveOutcome {
+    PcgScalars hs;
+    double bb = 0.0;
+};
+
+// Runs CG over `ranks` (size 1 in production).  All ranks see identical scalars.
+static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const mag_options &opt) {
+    const int format = opt.spmv_format == 1 ? 1 : 2;
+    const bool compat = opt.compat != 0;
+    const int jacobi = compat ? 0 : (opt.precond != 0);
+    int chunk = opt.check_every > 0 ? opt.check_every : 50;
+    chunk += chunk & 1;   // iteration parity is baked into the graph: even chunk length
+    SolveOutcome out;
+    std::memset(&out.hs, 0, sizeof out.hs);
+    PcgScalars &hs = out.hs;
+    const uint32_t n_glob = ranks[0].S->n_free;
+    if (n_glob == 0) { hs.stop = 1; return out; }
+
+    for (RankState &W : ranks)
+        if (W.n)
+            MAG_LAUNCH(ctx, pcg_init_kernel, W.grid_vec, 256, 0, W.x.p, W.r_ext, W.dinv_ext,
+                       (const double *)W.S->rhs.p, (const double *)W.S->diag.p, jacobi, W.n, W.S->row_lo,
+                       W.S->push, W.partials.p, W.scal.p);
+    reduce_scalars(ctx, ranks, kOffPair0, 2);      // also orders the halo stores before their readers
+    for (RankState &W : ranks)
+        MAG_LAUNCH(ctx, pcg_init_p_kernel, W.grid_ext, 256, 0, W.p_ext.p, (const double *)W.r_ext,
+                   (const double *)W.dinv_ext, W.S->ext_lo, W.S->ext_hi);
+    MAG_CUDA(cudaMemcpyAsync(&hs, ranks[0].scal.p, sizeof hs, cudaMemcpyDeviceToHost, ctx->stream));
+    MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double bb = hs.pair[0][1];
+    out.bb = bb;
+    const double thr2 = compat ? (opt.cost_kind == 1 ? opt.abs_tol : opt.abs_tol * opt.abs_tol)
+                               : opt.rel_tol * opt.rel_tol * bb;
+    int stop0 = 0;
+    if (!(bb == bb)) stop0 = 3;                         // NaN right-hand side
+    else if (bb <= thr2) stop0 = 1;                     // argmin: the initial cost is already <= target
+    else if (opt.max_iter == 0) stop0 = 2;
+    for (RankState &W : ranks) {
+        PcgScalars init;
+        std::memset(&init, 0, sizeof init);
+        init.pair[0][0] = hs.pair[0][0]; init.pair[0][1] = hs.pair[0][1];
+        init.thr2 = thr2; init.max_iter = opt.max_iter; init.stop = stop0;
+        MAG_CUDA(cudaMemcpyAsync(W.scal.p, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+    hs.thr2 = thr2; hs.stop = stop0; hs.iter = 0;
+    if (stop0) return out;
+
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const uint64_t l0 = ctx->launches;
+    MAG_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    try {
+        for (int i = 0; i < chunk; ++i) enqueue_iteration(ctx, ranks, i & 1, format);
+    } catch (...) {
+        cudaStreamEndCapture(ctx->stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+    }
+    MAG_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
+    const uint64_t per_chunk = ctx->launches - l0;
+    ctx->launches = l0;
+    MAG_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    static_assert(2 * sizeof(PcgScalars) <= 64 * sizeof(double), "pinned scratch too small");
+    PcgScalars *slot[2] = {reinterpret_cast<PcgScalars *>(ctx->h_scal),
+                           reinterpret_cast<PcgScalars *>(ctx->h_scal) + 1};
+    cudaEvent_t ev[2];
+    MAG_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    MAG_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    uint64_t queued = 0;
+    try {
+        for (uint64_t c = 0;; ++c) {
+            const int s = (int)(c & 1);
+            MAG_CUDA(cudaGraphLaunch(exec, ctx->stream));
+            ctx->launches += per_chunk;
+            MAG_CUDA(cudaMemcpyAsync(slot[s], ranks[0].scal.p, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
+            MAG_CUDA(cudaEventRecord(ev[s], ctx->stream));
+            queued += (uint64_t)chunk;
+            if (c > 0) {           // look at the previous chunk while this one runs
+                MAG_CUDA(cudaEventSynchronize(ev[s ^ 1]));
+                if (slot[s ^ 1]->stop) break;
+            }
+            if (queued >= opt.max_iter + (uint64_t)chunk) break;
+        }
+        MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+    } catch (...) {
+        cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+        cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+        throw;
+    }
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    MAG_CUDA(cudaMemcpyAsync(&hs, ranks[0].scal.p, sizeof hs, cudaMemcpyDeviceToHost, ctx->stream));
+    MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return out;
+}
+
+static void fill_solve_stats(mag_stats &st, const SolveOutcome &o, uint32_t n_glob) {
+    const PcgScalars &hs = o.hs;
+    const int last = (int)(hs.iter & 1);      // pair[] slot written by the last completed iteration
+    st.iters = hs.iter;
+    st.b_norm = std::sqrt(o.bb);
+    st.final_residual = std::sqrt(hs.iter ? hs.pair[last][1] : o.bb);
+    st.converged = (hs.stop == 1) || n_glob == 0;
+    st.negative_definite = hs.first_pq < 0.0;
+}
+
+// Post-processing shared by both drivers: full displacement field from the full solution
+// vector, reactions for the owned nodes, stresses for all elements (solver.rs:444-482, 496-535).
+struct PostBuffers {
+    DevBuf<double> xfull, ux, uy, fx, fy, stress, sigma;
+};
+
+static void post_local(mag_ctx *ctx, mag_system *S, PostBuffers &B, bool want_sigma) {
+    const size_t N = S->n_nodes, E = S->n_elems;
+    if (N) {
+        MAG_LAUNCH(ctx, scatter_solution_kernel, cdiv(N, 256), 256, 0, (const uint8_t *)S->known.p,
+                   (const uint32_t *)S->colmap.p, (const double *)S->bc_ux.p, (const double *)S->bc_uy.p,
+                   (const double *)B.xfull.p, N, B.ux.p, B.uy.p);
+        const uint32_t n_owned_dof = 2 * (S->K.node_hi - S->K.node_lo);
+        if (n_owned_dof)
+            MAG_LAUNCH(ctx, reactions_kernel, cdiv(n_owned_dof, 256), 256, 0, (const uint32_t *)S->K.browptr.p,
+                       (const uint32_t *)S->K.bcol.p, (const double *)S->K.bval.p, S->K.node_lo, n_owned_dof,
+                       (const uint8_t *)S->known.p, (const double *)S->bc_fx.p, (const double *)S->bc_fy.p,
+                       (const double *)B.ux.p, (const double *)B.uy.p, B.fx.p, B.fy.p);
+    }
+    if (E) {
+        upload_material(ctx, S->mat);
+        MAG_LAUNCH(ctx, stress_kernel, cdiv(E, 256), 256, 0, (const double2 *)S->xy.p,
+                   (const uint32_t *)S->n0.p, (const uint32_t *)S->n1.p, (const uint32_t *)S->n2.p, E,
+                   (const double *)B.ux.p, (const double *)B.uy.p, B.stress.p, want_sigma ? B.sigma.p : nullptr);
+    }
+}
+
+static void check_result_args(const mag_system *S, const mag_result *out) {
+    if (!out) fail(MAG_ERR_BAD_ARG, "null result");
+    if (S->n_nodes && (!out->ux || !out->uy || !out->fx || !out->fy)) fail(MAG_ERR_BAD_ARG, "result: ux, uy, fx, fy are required");
+    if (S->n_elems && !out->stress) fail(MAG_ERR_BAD_ARG, "result: stress is required");
+}
+
+static void download_result(mag_ctx *ctx, const mag_system *S, PostBuffers &B, mag_result *out, bool want_sigma) {
+    const size_t N = S->n_nodes, E = S->n_elems;
+    const bool odev = out->on_device != 0;
+    copy_from_device(ctx, out->ux, (const double *)B.ux.p, N, odev);
+    copy_from_device(ctx, out->uy, (const double *)B.uy.p, N, odev);
+    copy_from_device(ctx, out->fx, (const double *)B.fx.p, N, odev);
+    copy_from_device(ctx, out->fy, (const double *)B.fy.p, N, odev);
+    copy_from_device(ctx, out->stress, (const double *)B.stress.p, E, odev);
+    if (want_sigma) copy_from_device(ctx, out->sigma, (const double *)B.sigma.p, E * 3, odev);
+}
+
+static void raise_solver_status(const SolveOutcome &o, const mag_stats &st) {
+    if (o.hs.stop == 3)
+        fail(MAG_ERR_INDEFINITE, "conjugate gradient broke down at iteration %llu (p.Ap = %g, r.r = %g)",
+             (unsigned long long)o.hs.iter, o.hs.pq, st.final_residual * st.final_residual);
+    if (o.hs.stop == 2)
+        fail(MAG_ERR_NOT_CONVERGED, "conjugate gradient stopped at max_iter = %llu with ||r|| = %g",
+             (unsigned long long)o.hs.iter, st.final_residual);
+}
+
+// Production solve: this process owns one rank of S->nranks.
+static void solve_impl(mag_system *S, const mag_options *opt_in, mag_result *out, mag_stats *stats_out) {
+    mag_ctx *ctx = S->ctx;
+    mag_options opt;
+    if (opt_in) opt = *opt_in; else mag_options_default(&opt);
+    check_result_args(S, out);
+    const size_t N = S->n_nodes, E = S->n_elems;
+    mag_stats st = S->stats;
+    const uint64_t launches_before = ctx->launches;
+    EventTimer phase(ctx->stream);
+
+    phase.start();
+    if (S->nranks > 1) setup_halo_ipc(ctx, S);
+    std::vector<RankState> ranks(1);
+    rank_alloc(ctx, ranks[0], S);
+    SolveOutcome o = pcg_drive(ctx, ranks, opt);
+    fill_solve_stats(st, o, S->n_free);
+    st.ms_solve = phase.stop();
+
+    phase.start();
+    const bool want_sigma = out->sigma != nullptr;
+    PostBuffers B;
+    B.xfull.alloc(ctx, ext_len(S));
+    B.ux.alloc(ctx, N); B.uy.alloc(ctx, N); B.fx.alloc(ctx, N); B.fy.alloc(ctx, N);
+    B.stress.alloc(ctx, E);
+    if (want_sigma) B.sigma.alloc(ctx, E * 3);
+    if (ranks[0].n)
+        MAG_CUDA(cudaMemcpyAsync(B.xfull.p + S->row_lo, ranks[0].x.p, (size_t)ranks[0].n * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+    allgather_slices(ctx, B.xfull.p, S->all_row_lo);
+    post_local(ctx, S, B, want_sigma);
+    if (S->nranks > 1) {          // every rank returns complete fx, fy
+        allgather_slices(ctx, B.fx.p, S->all_node_lo);
+        allgather_slices(ctx, B.fy.p, S->all_node_lo);
+    }
+    st.ms_post = phase.stop();
+
+    phase.start();
+    download_result(ctx, S, B, out, want_sigma);
+    st.ms_download = phase.stop();
+    st.kernel_launches = ctx->launches - launches_before;
+    S->stats.iters = st.iters;
+    if (stats_out) *stats_out = st;
+    raise_solver_status(o, st);
+}
+
+// Single-process emulation of an R-rank solve on one GPU (tests): the mesh is assembled R
+// times, once per row block, and the blocks are driven in lockstep.
+static void virtual_solve_impl(mag_ctx *ctx, const mag_mesh *mesh, const mag_material *mat,
+                               const mag_options *opt_in, int R, mag_result *out, mag_stats *stats_out) {
+    if (R < 1 || R > 16) fail(MAG_ERR_BAD_ARG, "virtual ranks must be in [1,16]");
+    mag_options opt;
+    if (opt_in) opt = *opt_in; else mag_options_default(&opt);
+    std::vector<std::unique_ptr<mag_system>> sys(R);
+    uint64_t launches = 0;
+    for (int r = 0; r < R; ++r) {
+        sys[r].reset(new mag_system);
+        assemble_impl(ctx, mesh, mat, &opt, sys[r].get(), r, R);
+        launches += ctx->launches;
+        ctx->launches = 0;
+    }
+    check_result_args(sys[0].get(), out);
+    std::vector<uint32_t> elo(R), ehi(R);
+    std::vector<double *> slabs(R);
+    for (int r = 0; r < R; ++r) {
+        ensure_shared_slab(sys[r].get());
+        elo[r] = sys[r]->ext_lo; ehi[r] = sys[r]->ext_hi; slabs[r] = sys[r]->shared_slab;
+    }
+    for (int r = 0; r < R; ++r) build_push_segments(sys[r].get(), elo, ehi, slabs);
+    std::vector<RankState> ranks(R);
+    for (int r = 0; r < R; ++r) rank_alloc(ctx, ranks[r], sys[r].get());
+    EventTimer phase(ctx->stream);
+    phase.start();
+    SolveOutcome o = pcg_drive(ctx, ranks, opt);
+    mag_stats st = sys[0]->stats;
+    fill_solve_stats(st, o, sys[0]->n_free);
+    st.ms_solve = phase.stop();
+    st.nnz = 0; st.nnz_structural = 0;
+    for (int r = 0; r < R; ++r) { st.nnz += sys[r]->Kff.nnz; st.nnz_structural += (uint64_t)sys[r]->K.n_blocks * 4; }
+
+    const size_t N = sys[0]->n_nodes, E = sys[0]->n_elems;
+    const bool want_sigma = out->sigma != nullptr;
+    PostBuffers B;
+    B.xfull.alloc(ctx, ext_len(sys[0].get()));
+    B.ux.alloc(ctx, N); B.uy.alloc(ctx, N); B.fx.alloc(ctx, N); B.fy.alloc(ctx, N);
+    B.stress.alloc(ctx, E);
+    if (want_sigma) B.sigma.alloc(ctx, E * 3);
+    for (int r = 0; r < R; ++r)
+        if (ranks[r].n)
+            MAG_CUDA(cudaMemcpyAsync(B.xfull.p + sys[r]->row_lo, ranks[r].x.p, (size_t)ranks[r].n * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+    for (int r = 0; r < R; ++r) post_local(ctx, sys[r].get(), B, want_sigma);   // each fills its own fx, fy rows
+    download_result(ctx, sys[0].get(), B, out, want_sigma);
+    MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+    st.kernel_launches = launches + ctx->launches;
+    if (stats_out) *stats_out = st;
+    raise_solver_status(o, st);
+}
+
+}  // namespace mag

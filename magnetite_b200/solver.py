@@ -180,6 +180,25 @@ def solve_soa(mesh: MeshSoA, meta: ModelMetadata, ctx: Optional[_lib.Context] = 
     return Solution(bufs["ux"], bufs["uy"], bufs["fx"], bufs["fy"], stress, sigma, st.as_dict())
 
 
+def virtual_rank_solve(mesh: MeshSoA, meta: ModelMetadata, nranks: int, ctx: Optional[_lib.Context] = None,
+                       options: Optional[MagOptions] = None) -> Solution:
+    """An `nranks`-way row-block partitioned solve emulated on ONE GPU (mag_debug_virtual_solve):
+    the partition, kernels and peer halo stores of the multi-GPU path, with the allreduce done by
+    a kernel.  Test hook."""
+    ctx = ctx or default_context()
+    m = mesh.normalised()
+    n, e = m.n_nodes, m.n_elems
+    ms, mat = _mesh_struct(m), _material(meta)
+    opt = options or default_options()
+    bufs = {k: np.empty(n, np.float64) for k in ("ux", "uy", "fx", "fy")}
+    stress = np.empty(e, np.float64)
+    res = MagResult(ptr(bufs["ux"]), ptr(bufs["uy"]), ptr(bufs["fx"]), ptr(bufs["fy"]), ptr(stress), None, 0)
+    st = MagStats()
+    check(load().mag_debug_virtual_solve(ctx.handle, C.byref(ms), C.byref(mat), C.byref(opt), nranks,
+                                         C.byref(res), C.byref(st)), "mag_debug_virtual_solve")
+    return Solution(bufs["ux"], bufs["uy"], bufs["fx"], bufs["fy"], stress, None, st.as_dict())
+
+
 def element_stiffness(mesh: MeshSoA, meta: ModelMetadata, ctx: Optional[_lib.Context] = None) -> np.ndarray:
     """K_e of every element, (E, 6, 6) row-major (solver.rs:263-278)."""
     ctx = ctx or default_context()

@@ -1,0 +1,47 @@
+"""torchrun worker: every rank solves the same plate through the comm-aware C ABI (row-block
+partition, NCCL allreduce, IPC halo stores); rank 0 compares with a single-GPU virtual-rank solve
+and the oracle.  Launched by tests/test_gpu_parity.py and by hand:
+
+    torchrun --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 tests/dist_gpu_check.py
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from magnetite_b200 import _lib, dist as mdist, meshgen, solver  # noqa: E402
+
+
+def main():
+    rank, world, local = mdist.init_process_group("nccl")
+    ctx = _lib.Context(local)
+    mdist.init_comm(ctx)
+    meta = meshgen.EXAMPLE_MATERIAL
+    for mesh in (meshgen.jitter(meshgen.plate(96, 64)), meshgen.plate(300, 200)):
+        opt = _lib.default_options(rel_tol=1e-12)
+        sol = solver.solve_soa(mesh, meta, ctx, opt)            # comm-aware: this rank's row block
+        sol2 = solver.solve_soa(mesh, meta, ctx, opt)
+        assert sol.ux.tobytes() == sol2.ux.tobytes(), "not deterministic run to run"
+        if rank == 0:
+            solo = _lib.Context(local)                          # no communicator: plain single-GPU solve
+            one = solver.solve_soa(mesh, meta, solo, opt)
+            u, u1 = np.concatenate([sol.ux, sol.uy]), np.concatenate([one.ux, one.uy])
+            err = np.linalg.norm(u - u1) / np.linalg.norm(u1)
+            ferr = np.abs(np.concatenate([sol.fx - one.fx, sol.fy - one.fy])).max() / np.abs(one.fx).max()
+            serr = np.abs(sol.stress - one.stress).max() / np.abs(one.stress).max()
+            print(f"rank0: {mesh.n_elems} elements, world {world}: iters {sol.stats['iters']} vs {one.stats['iters']}, "
+                  f"|du| {err:.2e}, |df| {ferr:.2e}, |ds| {serr:.2e}", flush=True)
+            assert err < 1e-9 and ferr < 1e-7 and serr < 1e-8
+            assert abs(int(sol.stats["iters"]) - int(one.stats["iters"])) <= 5
+            solo.close()
+    import torch.distributed as dist
+    dist.barrier()
+    if rank == 0:
+        print("DIST_OK", flush=True)
+    ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
