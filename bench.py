@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--spmv-reps", type=int, default=100)
+    ap.add_argument("--allreduce", type=int, default=0, help="multi-GPU dot products: 0 peer-memory mailbox, 1 NCCL")
     return ap.parse_args()
 
 
@@ -197,7 +198,7 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     meta = meshgen.EXAMPLE_MATERIAL
     mat = _material(meta)
-    opt = _lib.default_options(stream=stream.cuda_stream)
+    opt = _lib.default_options(stream=stream.cuda_stream, allreduce=args.allreduce)
     nx, ny = args.nx, args.ny
 
     # ---- device-resident workload ------------------------------------------------------
@@ -322,7 +323,8 @@ def run_ours(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(nx, ny),
                    "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: contiguous row blocks, P2P halo stores fused "
-                                  f"into the CG update kernel, NCCL allreduce for the dot products",
+                                  f"into the CG update kernel, dot products allreduced "
+                                  f"{'by NCCL' if args.allreduce else 'through peer-memory mailboxes inside the CG kernels'}",
                    "l2": "inputs larger than L2 (K_ff + vectors >> 126 MB), no flush needed",
                    "solver": "Jacobi-PCG, rel_tol 1e-9, SELL-32 SpMV", "n_free": int(last.n_free),
                    "nnz": int(last.nnz), "nnz_structural": int(last.nnz_structural)},

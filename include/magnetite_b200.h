@@ -87,7 +87,7 @@ typedef struct {
     int32_t check_every;     /* iterations per CUDA-graph chunk between residual polls */
     int32_t spmv_format;     /* 0 auto, 1 scalar CSR, 2 SELL-32                        */
     int32_t want_sigma;      /* also return sx,sy,txy per element                      */
-    int32_t reserved;
+    int32_t allreduce;       /* multi-GPU dot products: 0 peer-memory mailbox (default), 1 NCCL  */
     void *stream;            /* cudaStream_t to run on, or NULL for the ctx's own      */
 } mag_options;
 

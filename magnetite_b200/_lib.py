@@ -42,7 +42,7 @@ class MagOptions(C.Structure):
     _fields_ = [("rel_tol", C.c_double), ("abs_tol", C.c_double), ("max_iter", C.c_uint64),
                 ("precond", C.c_int32), ("compat", C.c_int32), ("cost_kind", C.c_int32),
                 ("drop_exact_zeros", C.c_int32), ("check_every", C.c_int32),
-                ("spmv_format", C.c_int32), ("want_sigma", C.c_int32), ("reserved", C.c_int32),
+                ("spmv_format", C.c_int32), ("want_sigma", C.c_int32), ("allreduce", C.c_int32),
                 ("stream", C.c_void_p)]
 
 

@@ -368,7 +368,7 @@ extern "C" int mag_system_spmv_bench(mag_system *sys, int format, int reps, floa
             if (format == 2 && n)
                 MAG_LAUNCH(ctx, pcg_spmv_kernel, grid, 256, 0, (const uint32_t *)L.slice_off.p,
                            (const int32_t *)L.col.p, (const double *)L.val.p, (const double *)dx.p, dy.p,
-                           L.n_rows, L.n_slices, L.row_lo, partials.p, scal.p);
+                           L.n_rows, L.n_slices, L.row_lo, 0, PeerLinks{}, partials.p, scal.p, &scal.p->pq);
             else
                 launch_spmv(ctx, sys, format, dx.p, dy.p);
         };

@@ -35,15 +35,79 @@
 namespace mag {
 
 struct PcgScalars {
-    double pair[2][2];   // pair[parity] = {r.z, r.r} entering an iteration of that parity
-    double pq;
+    double pair[2][2];   // pair[parity] = {r.z, r.r} entering an iteration of that parity (global sums)
+    double pq;           // global p.q
+    double loc_pair[2];  // this rank's partial sums (send buffers of the NCCL fallback)
+    double loc_pq;
     double thr2;         // stop when r.r <= thr2
     double first_pq;     // its sign tells negative-definite systems
     unsigned long long iter, max_iter;
-    int stop;            // 1: converged, 2: max_iter, 3: breakdown
+    unsigned long long epoch;   // solve counter: makes mailbox sequence numbers unique across solves
+    int stop;            // 1: converged, 2: max_iter, 3: breakdown, 4: peer timeout
     unsigned ticket_a, ticket_b;
     int pad;
 };
+
+// ---- allreduce over peer memory ---------------------------------------------
+// Every rank owns a mailbox (in its IPC-exported slab).  The last CTA of the kernel
+// that finishes a local dot product stores {v0, v1, seq} into slot [kind][parity][me]
+// of EVERY rank's mailbox (NVLink peer stores); the kernel that needs the global value
+// polls the R slots of its OWN mailbox and adds them in rank order, so all ranks get
+// the bit-identical sum.  seq = epoch<<32 | iteration+1 never repeats, nothing is ever
+// reset, and a slot cannot be overwritten before it is consumed: the writer's next
+// message of the same kind depends on a message the reader sends after consuming.
+// One producer fence.sys + flag store orders the halo stores of the whole kernel.
+constexpr int kMaxRanks = 16;
+struct MailSlot { double v[2]; unsigned long long seq; unsigned long long pad; };
+constexpr int kMailSlots = 2 * 2 * kMaxRanks;     // [kind][parity][src]
+struct PeerLinks {
+    int n = 0, me = 0;                 // n == 0: single rank (or NCCL / emulated allreduce)
+    MailSlot *box[kMaxRanks];          // box[r]: rank r's mailbox as mapped in this process
+};
+enum { kMailPq = 0, kMailPair = 1 };
+
+__device__ __forceinline__ unsigned long long mail_seq(const PcgScalars *sc, unsigned long long it_plus) {
+    return (sc->epoch << 32) | it_plus;
+}
+
+// Called by all threads of the CTA that holds the local sums (v0, v1 valid in thread 0).
+__device__ __forceinline__ void mailbox_post(const PeerLinks &L, int kind, int parity, double v0, double v1,
+                                             unsigned long long seq) {
+    __shared__ double sv[2];
+    if (threadIdx.x == 0) { sv[0] = v0; sv[1] = v1; }
+    __syncthreads();
+    if ((int)threadIdx.x < L.n) {
+        volatile MailSlot *s = L.box[threadIdx.x] + (kind * 2 + parity) * kMaxRanks + L.me;
+        __threadfence_system();        // everything this kernel stored (incl. halo) before the flag
+        s->v[0] = sv[0];
+        s->v[1] = sv[1];
+        __threadfence_system();
+        s->seq = seq;
+    }
+}
+
+// Called by all threads of a CTA; returns the global sums.  A peer that never answers
+// (crashed rank) trips the timeout instead of hanging the GPU.
+__device__ __forceinline__ double2 mailbox_gather(const PeerLinks &L, int kind, int parity,
+                                                  unsigned long long seq, PcgScalars *sc) {
+    __shared__ double sg[2];
+    if (threadIdx.x == 0) {
+        const volatile MailSlot *mine = L.box[L.me] + (kind * 2 + parity) * kMaxRanks;
+        double a = 0.0, b = 0.0;
+        const long long t0 = clock64();
+        for (int r = 0; r < L.n; ++r) {
+            while (mine[r].seq != seq) {
+                if (clock64() - t0 > 60000000000ll) { sc->stop = 4; break; }   // ~30 s
+            }
+            __threadfence_system();
+            a += mine[r].v[0];
+            b += mine[r].v[1];
+        }
+        sg[0] = a; sg[1] = b;
+    }
+    __syncthreads();
+    return make_double2(sg[0], sg[1]);
+}
 
 constexpr int kMaxPush = 16;
 // Index ranges [lo,hi) of MY rows (global reduced index) that other ranks read as
@@ -64,19 +128,25 @@ __global__ void __launch_bounds__(256, 6)
 pcg_spmv_kernel(const uint32_t *__restrict__ slice_off, const int32_t *__restrict__ scol,
                 const double *__restrict__ sval, const double *__restrict__ p,
                 double *__restrict__ q, uint32_t n_rows, uint32_t n_slices, uint32_t row_lo,
-                double *__restrict__ partials, PcgScalars *__restrict__ sc) {
+                int parity, PeerLinks links, double *__restrict__ partials, PcgScalars *sc,
+                double *pq_out) {
     if (sc->stop) return;
     double v[1] = {sell_rows<true>(slice_off, scol, sval, p, q, n_rows, n_slices, row_lo)};
-    double tot[1];
-    if (grid_sum_256<1>(v, partials, &sc->ticket_a, tot)) sc->pq = tot[0];
+    double tot[1] = {0.0};
+    const bool last = grid_sum_256<1>(v, partials, &sc->ticket_a, tot);
+    if (links.n) {
+        if (grid_is_last_cta()) mailbox_post(links, kMailPq, parity, tot[0], 0.0, mail_seq(sc, sc->iter + 1));
+    } else if (last) {
+        *pq_out = tot[0];
+    }
 }
 
 // same, scalar CSR (format comparison)
 __global__ void __launch_bounds__(256)
 pcg_spmv_csr_kernel(const uint32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                     const double *__restrict__ val, const double *__restrict__ p,
-                    double *__restrict__ q, uint32_t n_rows, uint32_t row_lo,
-                    double *__restrict__ partials, PcgScalars *__restrict__ sc) {
+                    double *__restrict__ q, uint32_t n_rows, uint32_t row_lo, int parity,
+                    PeerLinks links, double *__restrict__ partials, PcgScalars *sc, double *pq_out) {
     if (sc->stop) return;
     double dot = 0.0;
     for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows;
@@ -87,17 +157,27 @@ pcg_spmv_csr_kernel(const uint32_t *__restrict__ rowptr, const int32_t *__restri
         dot = fma(__ldg(p + row_lo + row), acc, dot);
     }
     double v[1] = {dot};
-    double tot[1];
-    if (grid_sum_256<1>(v, partials, &sc->ticket_a, tot)) sc->pq = tot[0];
+    double tot[1] = {0.0};
+    const bool last = grid_sum_256<1>(v, partials, &sc->ticket_a, tot);
+    if (links.n) {
+        if (grid_is_last_cta()) mailbox_post(links, kMailPq, parity, tot[0], 0.0, mail_seq(sc, sc->iter + 1));
+    } else if (last) {
+        *pq_out = tot[0];
+    }
 }
 
 __global__ void __launch_bounds__(256)
 pcg_update_xr_kernel(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
                      const double *__restrict__ q, const double *__restrict__ dinv, uint32_t n,
-                     uint32_t row_lo, int parity, PushSegs push, double *__restrict__ partials,
-                     PcgScalars *__restrict__ sc) {
+                     uint32_t row_lo, int parity, PushSegs push, PeerLinks links,
+                     double *__restrict__ partials, PcgScalars *sc, double *pair_out) {
     if (sc->stop) return;
-    const double alpha = sc->pair[parity][0] / sc->pq;
+    double pq = sc->pq;
+    if (links.n) {
+        pq = mailbox_gather(links, kMailPq, parity, mail_seq(sc, sc->iter + 1), sc).x;
+        if (blockIdx.x == 0 && threadIdx.x == 0) sc->pq = pq;
+    }
+    const double alpha = sc->pair[parity][0] / pq;
     double v[2] = {0.0, 0.0};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t gi = row_lo + i;
@@ -109,10 +189,13 @@ pcg_update_xr_kernel(double *__restrict__ x, double *__restrict__ r, const doubl
         v[0] = fma(ri * dinv[gi], ri, v[0]);   // r.z with z = Dinv r
         v[1] = fma(ri, ri, v[1]);
     }
-    double tot[2];
-    if (grid_sum_256<2>(v, partials, &sc->ticket_b, tot)) {
-        sc->pair[parity ^ 1][0] = tot[0];
-        sc->pair[parity ^ 1][1] = tot[1];
+    double tot[2] = {0.0, 0.0};
+    const bool last = grid_sum_256<2>(v, partials, &sc->ticket_b, tot);
+    if (links.n) {
+        if (grid_is_last_cta()) mailbox_post(links, kMailPair, parity, tot[0], tot[1], mail_seq(sc, sc->iter + 1));
+    } else if (last) {
+        pair_out[0] = tot[0];
+        pair_out[1] = tot[1];
     }
 }
 
@@ -120,15 +203,22 @@ pcg_update_xr_kernel(double *__restrict__ x, double *__restrict__ r, const doubl
 __global__ void __launch_bounds__(256)
 pcg_update_p_kernel(double *__restrict__ p, const double *__restrict__ r,
                     const double *__restrict__ dinv, uint32_t ext_lo, uint32_t ext_hi, int parity,
-                    PcgScalars *__restrict__ sc) {
+                    PeerLinks links, PcgScalars *sc) {
     if (sc->stop) return;
-    const double rz_new = sc->pair[parity ^ 1][0], rr = sc->pair[parity ^ 1][1];
+    double rz_new = sc->pair[parity ^ 1][0], rr = sc->pair[parity ^ 1][1];
+    if (links.n) {
+        const double2 g = mailbox_gather(links, kMailPair, parity, mail_seq(sc, sc->iter + 1), sc);
+        rz_new = g.x; rr = g.y;
+    }
     const double rz_old = sc->pair[parity][0], pq = sc->pq;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->pair[parity ^ 1][0] = rz_new;
+        sc->pair[parity ^ 1][1] = rr;
         const unsigned long long it = sc->iter + 1;
         if (sc->iter == 0) sc->first_pq = pq;
         sc->iter = it;
-        if (!(pq != 0.0) || !(rr == rr)) sc->stop = 3;          // breakdown / NaN
+        if (sc->stop == 4) {}                                   // a peer never answered
+        else if (!(pq != 0.0) || !(rr == rr)) sc->stop = 3;     // breakdown / NaN
         else if (rr <= sc->thr2) sc->stop = 1;
         else if (it >= sc->max_iter) sc->stop = 2;
     }
@@ -144,8 +234,8 @@ pcg_update_p_kernel(double *__restrict__ p, const double *__restrict__ r,
 __global__ void __launch_bounds__(256)
 pcg_init_kernel(double *__restrict__ x, double *__restrict__ r, double *__restrict__ dinv,
                 const double *__restrict__ b, const double *__restrict__ diag, int jacobi, uint32_t n,
-                uint32_t row_lo, PushSegs push, double *__restrict__ partials,
-                PcgScalars *__restrict__ sc) {
+                uint32_t row_lo, PushSegs push, PeerLinks links, double *__restrict__ partials,
+                PcgScalars *sc, double *pair_out) {
     double v[2] = {0.0, 0.0};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t gi = row_lo + i;
@@ -159,16 +249,24 @@ pcg_init_kernel(double *__restrict__ x, double *__restrict__ r, double *__restri
         v[0] = fma(bi * di, bi, v[0]);
         v[1] = fma(bi, bi, v[1]);
     }
-    double tot[2];
-    if (grid_sum_256<2>(v, partials, &sc->ticket_b, tot)) {
-        sc->pair[0][0] = tot[0];
-        sc->pair[0][1] = tot[1];
+    double tot[2] = {0.0, 0.0};
+    const bool last = grid_sum_256<2>(v, partials, &sc->ticket_b, tot);
+    if (links.n) {
+        if (grid_is_last_cta()) mailbox_post(links, kMailPair, 0, tot[0], tot[1], mail_seq(sc, 0));
+    } else if (last) {
+        pair_out[0] = tot[0];
+        pair_out[1] = tot[1];
     }
 }
 
 // p = Dinv r over owned + halo rows (after the neighbours' pushes are visible)
-__global__ void pcg_init_p_kernel(double *__restrict__ p, const double *__restrict__ r,
-                                  const double *__restrict__ dinv, uint32_t ext_lo, uint32_t ext_hi) {
+__global__ void __launch_bounds__(256)
+pcg_init_p_kernel(double *__restrict__ p, const double *__restrict__ r, const double *__restrict__ dinv,
+                  uint32_t ext_lo, uint32_t ext_hi, PeerLinks links, PcgScalars *sc) {
+    if (links.n) {
+        const double2 g = mailbox_gather(links, kMailPair, 0, mail_seq(sc, 0), sc);
+        if (blockIdx.x == 0 && threadIdx.x == 0) { sc->pair[0][0] = g.x; sc->pair[0][1] = g.y; }
+    }
     const uint32_t n = ext_hi - ext_lo;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         p[ext_lo + i] = r[ext_lo + i] * dinv[ext_lo + i];
@@ -176,14 +274,14 @@ __global__ void pcg_init_p_kernel(double *__restrict__ p, const double *__restri
 
 // Single-process emulation of an allreduce(sum) over R virtual ranks: sums `count`
 // doubles at byte offset `off` of every rank's PcgScalars in rank order and
-// writes the result back to all of them.  (Tests only.)
+// writes the result to offset dst of all of them.  (Tests only.)
 struct ScalPtrs { int n; PcgScalars *p[16]; };
-__global__ void emulated_allreduce_kernel(ScalPtrs sp, int off_doubles, int count) {
+__global__ void emulated_allreduce_kernel(ScalPtrs sp, int src_off, int dst_off, int count) {
     const int j = threadIdx.x;
     if (j >= count) return;
     double s = 0.0;
-    for (int r = 0; r < sp.n; ++r) s += reinterpret_cast<double *>(sp.p[r])[off_doubles + j];
-    for (int r = 0; r < sp.n; ++r) reinterpret_cast<double *>(sp.p[r])[off_doubles + j] = s;
+    for (int r = 0; r < sp.n; ++r) s += reinterpret_cast<double *>(sp.p[r])[src_off + j];
+    for (int r = 0; r < sp.n; ++r) reinterpret_cast<double *>(sp.p[r])[dst_off + j] = s;
 }
 
 // [min, max] of the column indices of a CSR block (halo extent of a rank)

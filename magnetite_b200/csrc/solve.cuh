@@ -23,11 +23,21 @@ struct RankState {
 };
 
 inline size_t ext_len(const mag_system *S) { return (size_t)S->n_free + 32; }
+inline size_t slab_bytes(const mag_system *S) {
+    return 2 * ext_len(S) * sizeof(double) + kMailSlots * sizeof(MailSlot);
+}
+inline MailSlot *slab_mailbox(const mag_system *S, double *slab) {
+    return reinterpret_cast<MailSlot *>(slab + 2 * ext_len(S));
+}
 
-// Allocates the slab other ranks store into (plain cudaMalloc so it can be exported).
+// Allocates the slab other ranks store into (plain cudaMalloc so it can be exported):
+// [ r (global-indexed) | Dinv (global-indexed) | mailbox ].  The mailbox starts zeroed and is
+// never reset afterwards (sequence numbers only grow).
 static void ensure_shared_slab(mag_system *S) {
     if (S->shared_slab) return;
-    MAG_CUDA(cudaMalloc((void **)&S->shared_slab, 2 * ext_len(S) * sizeof(double)));
+    MAG_CUDA(cudaMalloc((void **)&S->shared_slab, slab_bytes(S)));
+    MAG_CUDA(cudaMemset(slab_mailbox(S, S->shared_slab), 0, kMailSlots * sizeof(MailSlot)));
+    MAG_CUDA(cudaDeviceSynchronize());
 }
 
 // Which of MY rows do the other ranks need?  Pure host logic (also exported as
@@ -80,19 +90,17 @@ static void setup_halo_ipc(mag_ctx *ctx, mag_system *S) {
     MAG_CUDA(cudaIpcGetMemHandle(&h, S->shared_slab));
     std::vector<cudaIpcMemHandle_t> hs(R);
     allgather_bytes(ctx, &h, sizeof h, hs.data());
+    if (R > kMaxRanks) fail(MAG_ERR_BAD_ARG, "at most %d ranks", kMaxRanks);
     std::vector<double *> peer(R, nullptr);
     for (int r = 0; r < R; ++r) {
         if (r == S->rank) { peer[r] = S->shared_slab; continue; }
-        // open only the ranks I actually store into
-        bool needed = false;
-        for (const HaloSeg &g : halo_plan(R, S->rank, S->all_row_lo.data(), elo.data(), ehi.data()))
-            needed = needed || g.dst == r;
-        if (!needed) continue;
-        void *p = nullptr;
+        void *p = nullptr;      // every rank is mapped: the mailbox allreduce posts to all of them
         MAG_CUDA(cudaIpcOpenMemHandle(&p, hs[r], cudaIpcMemLazyEnablePeerAccess));
         S->ipc_opened.push_back(p);
         peer[r] = static_cast<double *>(p);
     }
+    S->links.n = R; S->links.me = S->rank;
+    for (int r = 0; r < R; ++r) S->links.box[r] = slab_mailbox(S, peer[r]);
     build_push_segments(S, elo, ehi, peer);
 }
 
@@ -118,44 +126,72 @@ static void rank_alloc(mag_ctx *ctx, RankState &W, mag_system *S) {
     W.scal.zero();
 }
 
-// Sum over ranks of `count` doubles at `field` inside PcgScalars.
-static void reduce_scalars(mag_ctx *ctx, std::vector<RankState> &ranks, size_t off_doubles, int count) {
-    if (ranks.size() > 1) {          // virtual ranks in one process
+// How the per-rank partial sums become global sums.
+enum class Reduce { kNone, kMailbox, kNccl, kEmulated };
+constexpr size_t kOffPair0 = offsetof(PcgScalars, pair) / sizeof(double);
+constexpr size_t kOffPq = offsetof(PcgScalars, pq) / sizeof(double);
+constexpr size_t kOffLocPair = offsetof(PcgScalars, loc_pair) / sizeof(double);
+constexpr size_t kOffLocPq = offsetof(PcgScalars, loc_pq) / sizeof(double);
+
+struct SolveMode {
+    Reduce reduce = Reduce::kNone;
+    int format = 2;
+};
+
+inline double *scal_field(RankState &W, size_t off_doubles) {
+    return reinterpret_cast<double *>(W.scal.p) + off_doubles;
+}
+// Where a kernel writes its sums: the global slot when nothing follows, the local slot otherwise.
+inline double *pq_target(RankState &W, const SolveMode &m) {
+    return scal_field(W, (m.reduce == Reduce::kNccl || m.reduce == Reduce::kEmulated) ? kOffLocPq : kOffPq);
+}
+inline double *pair_target(RankState &W, const SolveMode &m, int slot) {
+    return scal_field(W, (m.reduce == Reduce::kNccl || m.reduce == Reduce::kEmulated) ? kOffLocPair
+                                                                                      : kOffPair0 + 2 * (size_t)slot);
+}
+inline PeerLinks links_of(RankState &W, const SolveMode &m) {
+    PeerLinks none;
+    none.n = 0; none.me = 0;
+    return m.reduce == Reduce::kMailbox ? W.S->links : none;
+}
+
+// loc -> global (count doubles) for the NCCL and emulated modes; a no-op otherwise.
+static void reduce_scalars(mag_ctx *ctx, std::vector<RankState> &ranks, const SolveMode &m, size_t src_off,
+                           size_t dst_off, int count) {
+    if (m.reduce == Reduce::kEmulated) {
         ScalPtrs sp;
         sp.n = (int)ranks.size();
         for (int r = 0; r < sp.n; ++r) sp.p[r] = ranks[r].scal.p;
-        MAG_LAUNCH(ctx, emulated_allreduce_kernel, 1, 32, 0, sp, (int)off_doubles, count);
-    } else {
-        allreduce_sum(ctx, reinterpret_cast<double *>(ranks[0].scal.p) + off_doubles, count);
+        MAG_LAUNCH(ctx, emulated_allreduce_kernel, 1, 32, 0, sp, (int)src_off, (int)dst_off, count);
+    } else if (m.reduce == Reduce::kNccl) {
+        Comm *c = ctx->comm;
+        MAG_NCCL(ncclAllReduce(scal_field(ranks[0], src_off), scal_field(ranks[0], dst_off), (size_t)count,
+                               ncclDouble, ncclSum, c->nccl, ctx->stream));
     }
 }
-constexpr size_t kOffPair0 = offsetof(PcgScalars, pair) / sizeof(double);
-constexpr size_t kOffPq = offsetof(PcgScalars, pq) / sizeof(double);
 
-static void enqueue_iteration(mag_ctx *ctx, std::vector<RankState> &ranks, int parity, int format) {
+static void enqueue_iteration(mag_ctx *ctx, std::vector<RankState> &ranks, int parity, const SolveMode &m) {
     for (RankState &W : ranks) {
         const SellMatrix &L = W.S->sell;
         const CsrMatrix &A = W.S->Kff;
-        if (!W.n) continue;
-        if (format == 1)
+        if (m.format == 1)
             MAG_LAUNCH(ctx, pcg_spmv_csr_kernel, W.grid_vec, 256, 0, (const uint32_t *)A.rowptr.p,
                        (const int32_t *)A.col.p, (const double *)A.val.p, (const double *)W.p_ext.p, W.q.p,
-                       W.n, A.row_lo, W.partials.p, W.scal.p);
+                       W.n, A.row_lo, parity, links_of(W, m), W.partials.p, W.scal.p, pq_target(W, m));
         else
             MAG_LAUNCH(ctx, pcg_spmv_kernel, W.grid_spmv, 256, 0, (const uint32_t *)L.slice_off.p,
                        (const int32_t *)L.col.p, (const double *)L.val.p, (const double *)W.p_ext.p, W.q.p,
-                       W.n, L.n_slices, L.row_lo, W.partials.p, W.scal.p);
+                       W.n, L.n_slices, L.row_lo, parity, links_of(W, m), W.partials.p, W.scal.p, pq_target(W, m));
     }
-    reduce_scalars(ctx, ranks, kOffPq, 1);
+    reduce_scalars(ctx, ranks, m, kOffLocPq, kOffPq, 1);
     for (RankState &W : ranks)
-        if (W.n)
-            MAG_LAUNCH(ctx, pcg_update_xr_kernel, W.grid_vec, 256, 0, W.x.p, W.r_ext, (const double *)W.p_ext.p,
-                       (const double *)W.q.p, (const double *)W.dinv_ext, W.n, W.S->row_lo, parity, W.S->push,
-                       W.partials.p, W.scal.p);
-    reduce_scalars(ctx, ranks, kOffPair0 + 2 * (size_t)(parity ^ 1), 2);
+        MAG_LAUNCH(ctx, pcg_update_xr_kernel, W.grid_vec, 256, 0, W.x.p, W.r_ext, (const double *)W.p_ext.p,
+                   (const double *)W.q.p, (const double *)W.dinv_ext, W.n, W.S->row_lo, parity, W.S->push,
+                   links_of(W, m), W.partials.p, W.scal.p, pair_target(W, m, parity ^ 1));
+    reduce_scalars(ctx, ranks, m, kOffLocPair, kOffPair0 + 2 * (size_t)(parity ^ 1), 2);
     for (RankState &W : ranks)
         MAG_LAUNCH(ctx, pcg_update_p_kernel, W.grid_ext, 256, 0, W.p_ext.p, (const double *)W.r_ext,
-                   (const double *)W.dinv_ext, W.S->ext_lo, W.S->ext_hi, parity, W.scal.p);
+                   (const double *)W.dinv_ext, W.S->ext_lo, W.S->ext_hi, parity, links_of(W, m), W.scal.p);
 }
 
 struct SolveOutcome {
@@ -165,7 +201,10 @@ struct SolveOutcome {
 
 // Runs CG over `ranks` (size 1 in production).  All ranks see identical scalars.
 static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const mag_options &opt) {
-    const int format = opt.spmv_format == 1 ? 1 : 2;
+    SolveMode mode;
+    mode.format = opt.spmv_format == 1 ? 1 : 2;
+    if (ranks.size() > 1) mode.reduce = Reduce::kEmulated;
+    else if (ranks[0].S->nranks > 1) mode.reduce = opt.allreduce == 1 ? Reduce::kNccl : Reduce::kMailbox;
     const bool compat = opt.compat != 0;
     const int jacobi = compat ? 0 : (opt.precond != 0);
     int chunk = opt.check_every > 0 ? opt.check_every : 50;
@@ -176,15 +215,21 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
     const uint32_t n_glob = ranks[0].S->n_free;
     if (n_glob == 0) { hs.stop = 1; return out; }
 
+    for (RankState &W : ranks) {
+        PcgScalars z;
+        std::memset(&z, 0, sizeof z);
+        z.epoch = ++W.S->solve_epoch;      // the same on every rank: solves are collective
+        MAG_CUDA(cudaMemcpyAsync(W.scal.p, &z, sizeof z, cudaMemcpyHostToDevice, ctx->stream));
+    }
     for (RankState &W : ranks)
-        if (W.n)
-            MAG_LAUNCH(ctx, pcg_init_kernel, W.grid_vec, 256, 0, W.x.p, W.r_ext, W.dinv_ext,
-                       (const double *)W.S->rhs.p, (const double *)W.S->diag.p, jacobi, W.n, W.S->row_lo,
-                       W.S->push, W.partials.p, W.scal.p);
-    reduce_scalars(ctx, ranks, kOffPair0, 2);      // also orders the halo stores before their readers
+        MAG_LAUNCH(ctx, pcg_init_kernel, W.grid_vec, 256, 0, W.x.p, W.r_ext, W.dinv_ext,
+                   (const double *)W.S->rhs.p, (const double *)W.S->diag.p, jacobi, W.n, W.S->row_lo,
+                   W.S->push, links_of(W, mode), W.partials.p, W.scal.p, pair_target(W, mode, 0));
+    // the reduction also orders the halo stores of r and Dinv before their readers
+    reduce_scalars(ctx, ranks, mode, kOffLocPair, kOffPair0, 2);
     for (RankState &W : ranks)
         MAG_LAUNCH(ctx, pcg_init_p_kernel, W.grid_ext, 256, 0, W.p_ext.p, (const double *)W.r_ext,
-                   (const double *)W.dinv_ext, W.S->ext_lo, W.S->ext_hi);
+                   (const double *)W.dinv_ext, W.S->ext_lo, W.S->ext_hi, links_of(W, mode), W.scal.p);
     MAG_CUDA(cudaMemcpyAsync(&hs, ranks[0].scal.p, sizeof hs, cudaMemcpyDeviceToHost, ctx->stream));
     MAG_CUDA(cudaStreamSynchronize(ctx->stream));
     const double bb = hs.pair[0][1];
@@ -200,6 +245,7 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
         std::memset(&init, 0, sizeof init);
         init.pair[0][0] = hs.pair[0][0]; init.pair[0][1] = hs.pair[0][1];
         init.thr2 = thr2; init.max_iter = opt.max_iter; init.stop = stop0;
+        init.epoch = W.S->solve_epoch;
         MAG_CUDA(cudaMemcpyAsync(W.scal.p, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
     }
     MAG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -211,7 +257,7 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
     const uint64_t l0 = ctx->launches;
     MAG_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
     try {
-        for (int i = 0; i < chunk; ++i) enqueue_iteration(ctx, ranks, i & 1, format);
+        for (int i = 0; i < chunk; ++i) enqueue_iteration(ctx, ranks, i & 1, mode);
     } catch (...) {
         cudaStreamEndCapture(ctx->stream, &graph);
         if (graph) cudaGraphDestroy(graph);
@@ -311,6 +357,9 @@ static void download_result(mag_ctx *ctx, const mag_system *S, PostBuffers &B, m
 }
 
 static void raise_solver_status(const SolveOutcome &o, const mag_stats &st) {
+    if (o.hs.stop == 4)
+        fail(MAG_ERR_NCCL, "a peer GPU never delivered its share of a dot product (iteration %llu): "
+                           "a rank has crashed or the ranks are out of step", (unsigned long long)o.hs.iter);
     if (o.hs.stop == 3)
         fail(MAG_ERR_INDEFINITE, "conjugate gradient broke down at iteration %llu (p.Ap = %g, r.r = %g)",
              (unsigned long long)o.hs.iter, o.hs.pq, st.final_residual * st.final_residual);

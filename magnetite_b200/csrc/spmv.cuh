@@ -93,11 +93,18 @@ inline void build_sell(mag_ctx *ctx, const CsrMatrix &A, SellMatrix &S) {
 // Every CTA writes its partial sum(s); the last CTA to arrive (ticket counter)
 // adds all partials in a fixed order, so the result does not depend on which
 // CTA happens to be last.  NV = number of simultaneous sums (1 or 2).
+// CTA-wide flag set by grid_sum_256: this CTA arrived last (one static __shared__ per kernel)
+__device__ __forceinline__ bool &cta_is_last_flag() {
+    __shared__ bool flag;
+    return flag;
+}
+__device__ __forceinline__ bool grid_is_last_cta() { return cta_is_last_flag(); }
+
 template <int NV>
 __device__ __forceinline__ bool grid_sum_256(double (&v)[NV], double *__restrict__ partials,
                                              unsigned *__restrict__ ticket, double (&total)[NV]) {
     __shared__ double red[NV][8];
-    __shared__ bool is_last;
+    bool &is_last = cta_is_last_flag();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -114,13 +121,13 @@ __device__ __forceinline__ bool grid_sum_256(double (&v)[NV], double *__restrict
             for (int w = 0; w < 8; ++w) s += red[i][w];
             partials[(size_t)i * gridDim.x + blockIdx.x] = s;
         }
-        __threadfence();
+        __threadfence_system();   // also orders this CTA's peer (halo) stores before the ticket
         const unsigned t = atomicAdd(ticket, 1u);
         is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
     if (!is_last) return false;
-    __threadfence();
+    __threadfence_system();
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         double s = 0.0;
@@ -141,6 +148,7 @@ __device__ __forceinline__ bool grid_sum_256(double (&v)[NV], double *__restrict
         }
         *ticket = 0;      // ready for the next launch
     }
+    __syncthreads();
     return threadIdx.x == 0;
 }
 

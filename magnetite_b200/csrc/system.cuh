@@ -42,6 +42,8 @@ struct mag_system {
     double *shared_slab = nullptr;           // [ r (n_free+32) | dinv (n_free+32) ], global-indexed
     std::vector<void *> ipc_opened;
     mag::PushSegs push;
+    mag::PeerLinks links;                    // peer mailboxes (production multi-rank only)
+    unsigned long long solve_epoch = 0;
     bool push_ready = false;
     std::vector<uint32_t> all_row_lo, all_node_lo;   // nranks+1
     mag_stats stats{};

@@ -46,7 +46,7 @@ pub mod sys {
         pub check_every: i32,
         pub spmv_format: i32,
         pub want_sigma: i32,
-        pub reserved: i32,
+        pub allreduce: i32,
         pub stream: *mut c_void,
     }
     #[repr(C)]

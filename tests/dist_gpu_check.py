@@ -18,8 +18,9 @@ def main():
     ctx = _lib.Context(local)
     mdist.init_comm(ctx)
     meta = meshgen.EXAMPLE_MATERIAL
-    for mesh in (meshgen.jitter(meshgen.plate(96, 64)), meshgen.plate(300, 200)):
-        opt = _lib.default_options(rel_tol=1e-12)
+    cases = [(meshgen.jitter(meshgen.plate(96, 64)), 0), (meshgen.plate(300, 200), 0), (meshgen.plate(300, 200), 1)]
+    for mesh, allreduce in cases:              # allreduce 0: peer-memory mailbox, 1: NCCL
+        opt = _lib.default_options(rel_tol=1e-12, allreduce=allreduce)
         sol = solver.solve_soa(mesh, meta, ctx, opt)            # comm-aware: this rank's row block
         sol2 = solver.solve_soa(mesh, meta, ctx, opt)
         assert sol.ux.tobytes() == sol2.ux.tobytes(), "not deterministic run to run"
@@ -30,7 +31,8 @@ def main():
             err = np.linalg.norm(u - u1) / np.linalg.norm(u1)
             ferr = np.abs(np.concatenate([sol.fx - one.fx, sol.fy - one.fy])).max() / np.abs(one.fx).max()
             serr = np.abs(sol.stress - one.stress).max() / np.abs(one.stress).max()
-            print(f"rank0: {mesh.n_elems} elements, world {world}: iters {sol.stats['iters']} vs {one.stats['iters']}, "
+            assert abs(sol.stats["final_residual"] - one.stats["final_residual"]) <= 1e-3 * one.stats["final_residual"]
+            print(f"rank0: {mesh.n_elems} elements, world {world}, allreduce {allreduce}: iters {sol.stats['iters']} vs {one.stats['iters']}, "
                   f"|du| {err:.2e}, |df| {ferr:.2e}, |ds| {serr:.2e}", flush=True)
             assert err < 1e-9 and ferr < 1e-7 and serr < 1e-8
             assert abs(int(sol.stats["iters"]) - int(one.stats["iters"])) <= 5
