@@ -115,6 +115,11 @@ typedef struct {
           ms_post, ms_download, ms_total;
     uint64_t kernel_launches;          /* launches issued by this call             */
     uint64_t spmv_bytes;               /* algorithmic bytes of one SpMV            */
+    /* device-side timeline of one CG iteration, ns, averaged over the solve (%globaltimer):
+     * 0 spmv.start - update_p.start(prev)   1 spmv duration       2 update_xr.start - spmv.end
+     * 3 update_xr wait for the global p.q   4 update_xr duration  5 update_p.start - update_xr.end
+     * 6 update_p wait for the global r.z    7 iterations timed                                  */
+    double prof[8];
 } mag_stats;
 
 typedef struct mag_ctx mag_ctx;        /* device + stream + memory pool + comm    */

@@ -61,10 +61,12 @@ class MagStats(C.Structure):
                 ("ms_reduce", C.c_float), ("ms_bc", C.c_float), ("ms_format", C.c_float),
                 ("ms_solve", C.c_float), ("ms_post", C.c_float), ("ms_download", C.c_float),
                 ("ms_total", C.c_float), ("kernel_launches", C.c_uint64),
-                ("spmv_bytes", C.c_uint64)]
+                ("spmv_bytes", C.c_uint64), ("prof", C.c_double * 8)]
 
     def as_dict(self) -> dict:
-        return {name: getattr(self, name) for name, _ in self._fields_}
+        d = {name: getattr(self, name) for name, _ in self._fields_}
+        d["prof"] = list(self.prof)
+        return d
 
 
 # every symbol include/magnetite_b200.h declares: (restype, argtypes)

@@ -3,6 +3,7 @@
 // contract and the reference lines each entry point replaces.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -92,6 +93,7 @@ extern "C" int mag_ctx_create(mag_ctx **out, int device) {
         MAG_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
         c->stream = c->own_stream;
         MAG_CUDA(cudaMallocHost((void **)&c->h_scal, 64 * sizeof(double)));
+        if (const char *t = std::getenv("MAG_TUNE")) c->tune = std::atoi(t);
         *out = c.release();
     });
 }

@@ -85,6 +85,7 @@ struct mag_ctx {
     cudaStream_t stream = nullptr;      // stream of the current call (own or caller's)
     mag::DeviceHeap heap;
     uint64_t launches = 0;              // kernels launched by the current call
+    int tune = 0;                       // MAG_TUNE debug switches (see PcgScalars::tune)
     mag::Comm *comm = nullptr;
     // pinned host scratch for scalar read-backs
     double *h_scal = nullptr;

@@ -14,29 +14,36 @@ struct RankState {
     mag_system *S = nullptr;
     uint32_t n = 0;                  // owned rows
     DevBuf<double> x, q;             // local
-    DevBuf<double> p_ext;            // global-indexed
-    DevBuf<double> own_slab;         // r|dinv when the system has no shared slab (single rank)
+    DevBuf<double> p_ext, r_store;   // global-indexed
+    DevBuf<double> dinv_store;       // Dinv when the system has no shared slab (single rank)
     double *r_ext = nullptr, *dinv_ext = nullptr;
+    HaloView halo;                   // my halo buffer (null for a single rank)
     DevBuf<double> partials;
     DevBuf<PcgScalars> scal;
     unsigned grid_vec = 1, grid_spmv = 1, grid_ext = 1;
 };
 
-inline size_t ext_len(const mag_system *S) { return (size_t)S->n_free + 32; }
+inline size_t ext_len(const mag_system *S) { return (((size_t)S->n_free + 32) + 15) & ~(size_t)15; }   // keeps the LL words 16-byte aligned
+inline size_t halo_count(const mag_system *S) {
+    return (size_t)(S->row_lo - S->ext_lo) + (size_t)(S->ext_hi - S->row_hi);
+}
+// Slab other ranks store into: [ Dinv (global-indexed) | mailbox | halo buffer of r (LL words) ]
 inline size_t slab_bytes(const mag_system *S) {
-    return 2 * ext_len(S) * sizeof(double) + kMailSlots * sizeof(MailSlot);
+    return ext_len(S) * sizeof(double) + kMailSlots * sizeof(MailSlot) + (halo_count(S) + 1) * sizeof(LLWord);
 }
 inline MailSlot *slab_mailbox(const mag_system *S, double *slab) {
-    return reinterpret_cast<MailSlot *>(slab + 2 * ext_len(S));
+    return reinterpret_cast<MailSlot *>(slab + ext_len(S));
+}
+inline LLWord *slab_halo(const mag_system *S, double *slab) {
+    return reinterpret_cast<LLWord *>(slab_mailbox(S, slab) + kMailSlots);
 }
 
-// Allocates the slab other ranks store into (plain cudaMalloc so it can be exported):
-// [ r (global-indexed) | Dinv (global-indexed) | mailbox ].  The mailbox starts zeroed and is
-// never reset afterwards (sequence numbers only grow).
+// Plain cudaMalloc so it can be exported through CUDA IPC.  Mailbox and halo buffer start
+// zeroed and are never reset afterwards (sequence numbers only move forward).
 static void ensure_shared_slab(mag_system *S) {
     if (S->shared_slab) return;
     MAG_CUDA(cudaMalloc((void **)&S->shared_slab, slab_bytes(S)));
-    MAG_CUDA(cudaMemset(slab_mailbox(S, S->shared_slab), 0, kMailSlots * sizeof(MailSlot)));
+    MAG_CUDA(cudaMemset(S->shared_slab, 0, slab_bytes(S)));
     MAG_CUDA(cudaDeviceSynchronize());
 }
 
@@ -65,13 +72,17 @@ static void build_push_segments(mag_system *S, const std::vector<uint32_t> &ext_
                                 const std::vector<double *> &peer_slab) {
     PushSegs &ps = S->push;
     ps.n = 0;
-    const size_t L = ext_len(S);
-    for (const HaloSeg &g : halo_plan(S->nranks, S->rank, S->all_row_lo.data(), ext_lo.data(), ext_hi.data())) {
+    const std::vector<uint32_t> &row = S->all_row_lo;
+    for (const HaloSeg &g : halo_plan(S->nranks, S->rank, row.data(), ext_lo.data(), ext_hi.data())) {
         if (ps.n == kMaxPush) fail(MAG_ERR_BAD_ARG, "halo pattern needs more than %d push segments", kMaxPush);
         if (!peer_slab[g.dst]) fail(MAG_ERR_BAD_ARG, "no mapping of rank %d's halo buffer", g.dst);
+        // slot of row g.lo in the destination's compact halo buffer: lower halo first, then upper
+        const uint32_t d_ext_lo = ext_lo[g.dst], d_row_lo = row[g.dst], d_row_hi = row[g.dst + 1];
+        const size_t slot = g.hi <= d_row_lo ? (size_t)(g.lo - d_ext_lo)
+                                             : (size_t)(g.lo - d_row_hi) + (size_t)(d_row_lo - d_ext_lo);
         ps.lo[ps.n] = g.lo; ps.hi[ps.n] = g.hi;
-        ps.r_dst[ps.n] = peer_slab[g.dst];
-        ps.dinv_dst[ps.n] = peer_slab[g.dst] + L;
+        ps.ll_dst[ps.n] = slab_halo(S, peer_slab[g.dst]) + slot;
+        ps.dinv_dst[ps.n] = peer_slab[g.dst];
         ++ps.n;
     }
     S->push_ready = true;
@@ -110,13 +121,16 @@ static void rank_alloc(mag_ctx *ctx, RankState &W, mag_system *S) {
     W.x.alloc(ctx, W.n); W.q.alloc(ctx, W.n);
     W.p_ext.alloc(ctx, ext_len(S));
     W.p_ext.zero();
+    W.r_store.alloc(ctx, ext_len(S));
+    W.r_ext = W.r_store.p;
     if (S->shared_slab) {
-        W.r_ext = S->shared_slab;
+        W.dinv_ext = S->shared_slab;
+        W.halo.ll = slab_halo(S, S->shared_slab);
+        W.halo.ext_lo = S->ext_lo; W.halo.row_lo = S->row_lo; W.halo.row_hi = S->row_hi;
     } else {
-        W.own_slab.alloc(ctx, 2 * ext_len(S));
-        W.r_ext = W.own_slab.p;
+        W.dinv_store.alloc(ctx, ext_len(S));
+        W.dinv_ext = W.dinv_store.p;
     }
-    W.dinv_ext = W.r_ext + ext_len(S);
     const unsigned cap = (unsigned)ctx->sm_count * 8u;
     W.grid_vec = std::max(1u, std::min(cdiv(W.n, 256), cap));
     W.grid_ext = std::max(1u, std::min(cdiv(S->ext_hi - S->ext_lo, 256), cap));
@@ -170,28 +184,29 @@ static void reduce_scalars(mag_ctx *ctx, std::vector<RankState> &ranks, const So
     }
 }
 
-static void enqueue_iteration(mag_ctx *ctx, std::vector<RankState> &ranks, int parity, const SolveMode &m) {
+static void enqueue_iteration(mag_ctx *ctx, std::vector<RankState> &ranks, int step, const SolveMode &m) {
+    const int parity = step & 1;
     for (RankState &W : ranks) {
         const SellMatrix &L = W.S->sell;
         const CsrMatrix &A = W.S->Kff;
         if (m.format == 1)
             MAG_LAUNCH(ctx, pcg_spmv_csr_kernel, W.grid_vec, 256, 0, (const uint32_t *)A.rowptr.p,
                        (const int32_t *)A.col.p, (const double *)A.val.p, (const double *)W.p_ext.p, W.q.p,
-                       W.n, A.row_lo, parity, links_of(W, m), W.partials.p, W.scal.p, pq_target(W, m));
+                       W.n, A.row_lo, step, links_of(W, m), W.partials.p, W.scal.p, pq_target(W, m));
         else
             MAG_LAUNCH(ctx, pcg_spmv_kernel, W.grid_spmv, 256, 0, (const uint32_t *)L.slice_off.p,
                        (const int32_t *)L.col.p, (const double *)L.val.p, (const double *)W.p_ext.p, W.q.p,
-                       W.n, L.n_slices, L.row_lo, parity, links_of(W, m), W.partials.p, W.scal.p, pq_target(W, m));
+                       W.n, L.n_slices, L.row_lo, step, links_of(W, m), W.partials.p, W.scal.p, pq_target(W, m));
     }
     reduce_scalars(ctx, ranks, m, kOffLocPq, kOffPq, 1);
     for (RankState &W : ranks)
         MAG_LAUNCH(ctx, pcg_update_xr_kernel, W.grid_vec, 256, 0, W.x.p, W.r_ext, (const double *)W.p_ext.p,
-                   (const double *)W.q.p, (const double *)W.dinv_ext, W.n, W.S->row_lo, parity, W.S->push,
+                   (const double *)W.q.p, (const double *)W.dinv_ext, W.n, W.S->row_lo, step, W.S->push,
                    links_of(W, m), W.partials.p, W.scal.p, pair_target(W, m, parity ^ 1));
     reduce_scalars(ctx, ranks, m, kOffLocPair, kOffPair0 + 2 * (size_t)(parity ^ 1), 2);
     for (RankState &W : ranks)
         MAG_LAUNCH(ctx, pcg_update_p_kernel, W.grid_ext, 256, 0, W.p_ext.p, (const double *)W.r_ext,
-                   (const double *)W.dinv_ext, W.S->ext_lo, W.S->ext_hi, parity, links_of(W, m), W.scal.p);
+                   (const double *)W.dinv_ext, W.S->ext_lo, W.S->ext_hi, step, W.halo, links_of(W, m), W.scal.p);
 }
 
 struct SolveOutcome {
@@ -219,6 +234,7 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
         PcgScalars z;
         std::memset(&z, 0, sizeof z);
         z.epoch = ++W.S->solve_epoch;      // the same on every rank: solves are collective
+        z.tune = ctx->tune;
         MAG_CUDA(cudaMemcpyAsync(W.scal.p, &z, sizeof z, cudaMemcpyHostToDevice, ctx->stream));
     }
     for (RankState &W : ranks)
@@ -229,7 +245,7 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
     reduce_scalars(ctx, ranks, mode, kOffLocPair, kOffPair0, 2);
     for (RankState &W : ranks)
         MAG_LAUNCH(ctx, pcg_init_p_kernel, W.grid_ext, 256, 0, W.p_ext.p, (const double *)W.r_ext,
-                   (const double *)W.dinv_ext, W.S->ext_lo, W.S->ext_hi, links_of(W, mode), W.scal.p);
+                   (const double *)W.dinv_ext, W.S->ext_lo, W.S->ext_hi, W.halo, links_of(W, mode), W.scal.p);
     MAG_CUDA(cudaMemcpyAsync(&hs, ranks[0].scal.p, sizeof hs, cudaMemcpyDeviceToHost, ctx->stream));
     MAG_CUDA(cudaStreamSynchronize(ctx->stream));
     const double bb = hs.pair[0][1];
@@ -246,6 +262,7 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
         init.pair[0][0] = hs.pair[0][0]; init.pair[0][1] = hs.pair[0][1];
         init.thr2 = thr2; init.max_iter = opt.max_iter; init.stop = stop0;
         init.epoch = W.S->solve_epoch;
+        init.tune = ctx->tune;
         MAG_CUDA(cudaMemcpyAsync(W.scal.p, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
     }
     MAG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -257,7 +274,8 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
     const uint64_t l0 = ctx->launches;
     MAG_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
     try {
-        for (int i = 0; i < chunk; ++i) enqueue_iteration(ctx, ranks, i & 1, mode);
+        for (int i = 0; i < chunk; ++i) enqueue_iteration(ctx, ranks, i, mode);
+        for (RankState &W : ranks) MAG_LAUNCH(ctx, pcg_chunk_end_kernel, 1, 1, 0, chunk, W.scal.p);
     } catch (...) {
         cudaStreamEndCapture(ctx->stream, &graph);
         if (graph) cudaGraphDestroy(graph);
@@ -309,6 +327,7 @@ static void fill_solve_stats(mag_stats &st, const SolveOutcome &o, uint32_t n_gl
     st.b_norm = std::sqrt(o.bb);
     st.final_residual = std::sqrt(hs.iter ? hs.pair[last][1] : o.bb);
     st.converged = (hs.stop == 1) || n_glob == 0;
+    for (int i = 0; i < 8; ++i) st.prof[i] = hs.prof[7] > 0 && i < 7 ? hs.prof[i] / hs.prof[7] : hs.prof[i];
     st.negative_definite = hs.first_pq < 0.0;
 }
 

@@ -102,7 +102,8 @@ __device__ __forceinline__ bool grid_is_last_cta() { return cta_is_last_flag(); 
 
 template <int NV>
 __device__ __forceinline__ bool grid_sum_256(double (&v)[NV], double *__restrict__ partials,
-                                             unsigned *__restrict__ ticket, double (&total)[NV]) {
+                                             unsigned *__restrict__ ticket, double (&total)[NV],
+                                             bool system_scope = false) {
     __shared__ double red[NV][8];
     bool &is_last = cta_is_last_flag();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -121,13 +122,14 @@ __device__ __forceinline__ bool grid_sum_256(double (&v)[NV], double *__restrict
             for (int w = 0; w < 8; ++w) s += red[i][w];
             partials[(size_t)i * gridDim.x + blockIdx.x] = s;
         }
-        __threadfence_system();   // also orders this CTA's peer (halo) stores before the ticket
+        if (system_scope) __threadfence_system();   // also orders this CTA's peer stores before the ticket
+        else __threadfence();
         const unsigned t = atomicAdd(ticket, 1u);
         is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
     if (!is_last) return false;
-    __threadfence_system();
+    if (system_scope) __threadfence_system(); else __threadfence();
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         double s = 0.0;

@@ -39,7 +39,7 @@ struct mag_system {
     mag::DevBuf<double> rhs, diag;           // owned rows
     mag::SellMatrix sell;
     // halo buffers other ranks store into (plain cudaMalloc: exported through CUDA IPC)
-    double *shared_slab = nullptr;           // [ r (n_free+32) | dinv (n_free+32) ], global-indexed
+    double *shared_slab = nullptr;           // [ Dinv (global-indexed) | mailbox | halo buffer of r ]
     std::vector<void *> ipc_opened;
     mag::PushSegs push;
     mag::PeerLinks links;                    // peer mailboxes (production multi-rank only)

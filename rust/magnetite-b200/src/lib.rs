@@ -69,6 +69,7 @@ pub mod sys {
         pub ms_upload: f32, pub ms_elem: f32, pub ms_sort: f32, pub ms_reduce: f32, pub ms_bc: f32,
         pub ms_format: f32, pub ms_solve: f32, pub ms_post: f32, pub ms_download: f32, pub ms_total: f32,
         pub kernel_launches: u64, pub spmv_bytes: u64,
+        pub prof: [f64; 8],
     }
     pub enum mag_ctx {}
 
