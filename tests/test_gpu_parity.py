@@ -319,3 +319,26 @@ def test_two_process_nccl_solve_matches_single_gpu(ctx):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "DIST_OK" in r.stdout
+
+
+@pytest.mark.parametrize("name", ["example_tensile", "example_linkedin", "example_cover"])
+def test_reference_example_configs(ctx, name):
+    """BASELINE configs 1-2: the reference's example geometries (stand-in mesher, reference input
+    semantics incl. check_ccw's all-clockwise tensile mesh) against the oracle in faithful-dense mode."""
+    g = np.load(GOLDEN / f"{name}.npz")
+    mesh = golden_mesh(g)
+    meta = META.__class__(*g["material"])
+    sol = solver.solve_soa(mesh, meta, ctx, compat())
+    u, ur = np.concatenate([sol.ux, sol.uy]), np.concatenate([g["ux"], g["uy"]])
+    assert rel_l2(u, ur) < 1e-9
+    assert np.abs(sol.stress - g["stress"]).max() / np.abs(g["stress"]).max() < 1e-8
+    f, fr = np.concatenate([sol.fx, sol.fy]), np.concatenate([g["fx"], g["fy"]])
+    assert np.abs(f - fr).max() / np.abs(fr).max() < 1e-8
+    assert sol.stats["nnz"] == int(g["nnz_ff"][0])
+    assert sol.stats["negative_definite"] == (1 if name == "example_tensile" else 0)
+    assert abs(int(sol.stats["iters"]) - int(g["iters"][0])) <= max(5, int(g["iters"][0]) // 20)
+    # the same mesh through the north-star solver (Jacobi-PCG) and through 4 virtual ranks
+    pcg = solver.solve_soa(mesh, meta, ctx, _lib.default_options(rel_tol=1e-13))
+    assert rel_l2(np.concatenate([pcg.ux, pcg.uy]), ur) < 1e-9
+    vr = solver.virtual_rank_solve(mesh, meta, 4, ctx, _lib.default_options(rel_tol=1e-13))
+    assert rel_l2(np.concatenate([vr.ux, vr.uy]), ur) < 1e-9
