@@ -1,0 +1,165 @@
+// magnetite_host.cpp — see magnetite_host.hpp.  Host-only C++17; links libmagnetite_b200.so.
+#include "magnetite_host.hpp"
+
+#include <charconv>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <fstream>
+
+#include "../include/magnetite_b200.h"
+
+namespace magnetite {
+
+static const char *kind_name(MagnetiteError::Kind k) {
+    switch (k) {
+        case MagnetiteError::Kind::Input: return "Input";
+        case MagnetiteError::Kind::Mesher: return "Mesher";
+        case MagnetiteError::Kind::Solver: return "Solver";
+        default: return "Post Processor";
+    }
+}
+
+MagnetiteError::MagnetiteError(Kind k, const std::string &msg, int c)
+    : std::runtime_error(std::string(kind_name(k)) + " error: " + msg), kind(k), code(c), message(msg) {}
+
+namespace {
+
+struct Ctx {                       // RAII around mag_ctx
+    mag_ctx *h = nullptr;
+    explicit Ctx(int device) {
+        const int rc = mag_ctx_create(&h, device);
+        if (rc != MAG_OK) throw MagnetiteError(MagnetiteError::Kind::Solver, mag_last_error(), rc);
+    }
+    ~Ctx() { mag_ctx_destroy(h); }
+};
+
+struct Flat {                      // Vec<Node>/Vec<Element> flattened for mag_mesh
+    std::vector<double> x, y, ux, uy, fx, fy;
+    std::vector<std::uint8_t> known;
+    std::vector<std::uint32_t> n0, n1, n2;
+    mag_mesh view() const {
+        mag_mesh m{};
+        m.n_nodes = x.size(); m.n_elems = n0.size();
+        m.x = x.data(); m.y = y.data();
+        m.n0 = n0.data(); m.n1 = n1.data(); m.n2 = n2.data();
+        m.ux = ux.data(); m.uy = uy.data(); m.fx = fx.data(); m.fy = fy.data();
+        m.known = known.data(); m.on_device = 0;
+        return m;
+    }
+};
+
+Flat flatten(const std::vector<Node> &nodes, const std::vector<Element> &elements) {
+    Flat f;
+    const std::size_t n = nodes.size(), e = elements.size();
+    f.x.resize(n); f.y.resize(n); f.ux.assign(n, 0.0); f.uy.assign(n, 0.0); f.fx.assign(n, 0.0); f.fy.assign(n, 0.0);
+    f.known.assign(n, 0);
+    for (std::size_t i = 0; i < n; ++i) {
+        const Node &nd = nodes[i];
+        f.x[i] = nd.vertex.x; f.y[i] = nd.vertex.y;
+        if (nd.ux) { f.ux[i] = *nd.ux; f.known[i] |= MAG_KNOWN_UX; }
+        if (nd.uy) { f.uy[i] = *nd.uy; f.known[i] |= MAG_KNOWN_UY; }
+        if (nd.fx) { f.fx[i] = *nd.fx; f.known[i] |= MAG_KNOWN_FX; }
+        if (nd.fy) { f.fy[i] = *nd.fy; f.known[i] |= MAG_KNOWN_FY; }
+    }
+    f.n0.resize(e); f.n1.resize(e); f.n2.resize(e);
+    for (std::size_t i = 0; i < e; ++i) {
+        for (std::size_t v : elements[i].nodes)
+            if (v > 0xfffffffeull) throw MagnetiteError(MagnetiteError::Kind::Solver, "node index does not fit 32 bits");
+        f.n0[i] = (std::uint32_t)elements[i].nodes[0];
+        f.n1[i] = (std::uint32_t)elements[i].nodes[1];
+        f.n2[i] = (std::uint32_t)elements[i].nodes[2];
+    }
+    return f;
+}
+
+}  // namespace
+
+namespace solver {
+
+void run(std::vector<Node> &nodes, std::vector<Element> &elements, const ModelMetadata &md,
+         const SolverOptions &so) {
+    auto say = [&](const char *s) { if (!so.quiet) std::printf("%s\n", s); };
+    say("info: building element stiffness matrices...");           // solver.rs:551
+    say("info: building total stiffness matrix...");               // solver.rs:570
+    const Flat f = flatten(nodes, elements);
+    const mag_mesh mesh = f.view();
+    const mag_material mat{md.youngs_modulus, md.poisson_ratio, md.part_thickness};
+    mag_options opt;
+    mag_options_default(&opt);
+    opt.compat = so.compat ? 1 : 0;
+    opt.rel_tol = so.rel_tol;
+    const std::size_t n = nodes.size(), e = elements.size();
+    std::vector<double> ux(n), uy(n), fx(n), fy(n), stress(e);
+    mag_result out{ux.data(), uy.data(), fx.data(), fy.data(), stress.data(), nullptr, 0};
+    mag_stats st{};
+    say("info: setting up system...");                             // solver.rs:416
+    say("info: solving...");                                       // solver.rs:437
+    {
+        Ctx ctx(so.device);
+        const int rc = mag_solve(ctx.h, &mesh, &mat, &opt, &out, &st);
+        if (rc != MAG_OK)                                          // solver.rs:160-164
+            throw MagnetiteError(MagnetiteError::Kind::Solver,
+                                 std::string("Conjugate Gradient error: ") + mag_last_error(), rc);
+    }
+    if (!so.quiet) {
+        std::printf("info: finished conjugate gradient approximation in %llu iterations\n",
+                    (unsigned long long)st.iters);                 // solver.rs:101-104
+        std::printf("info: solved system in %.3f seconds\n", st.ms_solve / 1e3);   // solver.rs:441
+    }
+    for (std::size_t i = 0; i < n; ++i) {                          // solver.rs:476-482
+        nodes[i].ux = ux[i]; nodes[i].uy = uy[i];
+        nodes[i].fx = fx[i]; nodes[i].fy = fy[i];
+    }
+    for (std::size_t i = 0; i < e; ++i) elements[i].stress = stress[i];   // solver.rs:532-533
+    say("info: solve complete");                                   // solver.rs:484
+}
+
+double compute_element_area(const Element &element, const std::vector<Node> &nodes) {
+    std::vector<Node> tri = {nodes.at(element.nodes[0]), nodes.at(element.nodes[1]), nodes.at(element.nodes[2])};
+    std::vector<Element> one = {Element{{0, 1, 2}, std::nullopt}};
+    const Flat f = flatten(tri, one);
+    const mag_mesh mesh = f.view();
+    double area = 0.0;
+    Ctx ctx(0);
+    const int rc = mag_element_area(ctx.h, &mesh, &area);
+    if (rc != MAG_OK) throw MagnetiteError(MagnetiteError::Kind::Solver, mag_last_error(), rc);
+    return area;
+}
+
+}  // namespace solver
+
+namespace post_processor {
+
+std::string format_f64(double v) {
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
+    char buf[400];
+    const auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);   // shortest round trip
+    return std::string(buf, r.ptr);
+}
+
+void csv_output(const std::vector<Element> &elements, const std::vector<Node> &nodes,
+                const std::string &nodes_output, const std::string &elements_output, bool quiet) {
+    std::ofstream nf(nodes_output, std::ios::binary | std::ios::trunc);
+    if (!nf) throw MagnetiteError(MagnetiteError::Kind::Solver, "Failed to create nodes.csv: " + nodes_output);
+    std::ofstream ef(elements_output, std::ios::binary | std::ios::trunc);
+    if (!ef) throw MagnetiteError(MagnetiteError::Kind::Solver, "Failed to create elements.csv: " + elements_output);
+    nf << "x,y,ux,uy\n";                                           // post_processor.rs:42
+    for (const Node &nd : nodes) {
+        if (!nd.ux || !nd.uy)                                      // the reference unwrap()s (:50-51)
+            throw MagnetiteError(MagnetiteError::Kind::PostProcessor, "node without a displacement: run the solver first");
+        nf << format_f64(nd.vertex.x) << ',' << format_f64(nd.vertex.y) << ',' << format_f64(*nd.ux) << ','
+           << format_f64(*nd.uy) << '\n';
+    }
+    ef << "n0,n1,n2,stress\n";                                     // post_processor.rs:60
+    for (const Element &el : elements) {
+        if (!el.stress)
+            throw MagnetiteError(MagnetiteError::Kind::PostProcessor, "element without a stress: run the solver first");
+        ef << el.nodes[0] << ',' << el.nodes[1] << ',' << el.nodes[2] << ',' << format_f64(*el.stress) << '\n';
+    }
+    if (!quiet) std::printf("info: wrote output to %s and %s\n", nodes_output.c_str(), elements_output.c_str());
+}
+
+}  // namespace post_processor
+}  // namespace magnetite

@@ -155,3 +155,14 @@ def test_meshgen_invariants():
     assert used.all() and p.n_elems < 2 * 64 * 32
     j = meshgen.jitter(m)
     assert (j.x != m.x).any() and np.array_equal(j.known, m.known)
+
+
+def test_cpp_host_layer_formats_like_rust(built):
+    """host/plate_demo (C++ mirror of solver::run / csv_output) — the float formatter and the error
+    Display need no GPU."""
+    import subprocess
+    exe = ROOT / "host" / "plate_demo"
+    if not exe.exists():
+        subprocess.run(["make", "-C", str(ROOT / "host")], check=True)
+    r = subprocess.run([str(exe), "--format-selftest"], capture_output=True, text=True)
+    assert r.returncode == 0 and "FORMAT_OK" in r.stdout, r.stdout + r.stderr

@@ -342,3 +342,21 @@ def test_reference_example_configs(ctx, name):
     assert rel_l2(np.concatenate([pcg.ux, pcg.uy]), ur) < 1e-9
     vr = solver.virtual_rank_solve(mesh, meta, 4, ctx, _lib.default_options(rel_tol=1e-13))
     assert rel_l2(np.concatenate([vr.ux, vr.uy]), ur) < 1e-9
+
+
+def test_cpp_host_layer_end_to_end(ctx, tmp_path):
+    """The C++ mirror of main.rs:54-76 (solver::run + csv_output over the C ABI) writes byte-identical
+    CSVs to the Python mirror: same library, deterministic kernels, same Rust-style float formatting."""
+    import subprocess
+    from magnetite_b200 import post_processor
+    root = Path(__file__).resolve().parent.parent
+    exe = root / "host" / "plate_demo"
+    r = subprocess.run([str(exe), "12", "6", str(tmp_path / "n_cpp.csv"), str(tmp_path / "e_cpp.csv")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "info: solve complete" in r.stdout and "area of element 0: 2" in r.stdout
+    nodes, elements = meshgen.plate(12, 6).to_aos()
+    solver.run(nodes, elements, META, quiet=True)
+    post_processor.csv_output(elements, nodes, str(tmp_path / "n_py.csv"), str(tmp_path / "e_py.csv"), quiet=True)
+    assert (tmp_path / "n_cpp.csv").read_bytes() == (tmp_path / "n_py.csv").read_bytes()
+    assert (tmp_path / "e_cpp.csv").read_bytes() == (tmp_path / "e_py.csv").read_bytes()
