@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--spmv-reps", type=int, default=100)
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
+                    help="c4: the 16 M-DOF plate (strong scaling); c5: perforated plate, 16 M DOF per GPU (weak scaling)")
     ap.add_argument("--allreduce", type=int, default=0, help="multi-GPU dot products: 0 peer-memory mailbox, 1 NCCL")
     return ap.parse_args()
 
@@ -200,10 +202,16 @@ def run_ours(args):
     mat = _material(meta)
     opt = _lib.default_options(stream=stream.cuda_stream, allreduce=args.allreduce)
     nx, ny = args.nx, args.ny
+    weak = args.workload == "c5"
+    if weak:                                   # BASELINE configs[4]: 16 M DOF per GPU, perforated
+        nx, ny = int(round(args.nx * world ** 0.5)), int(round(args.ny * world ** 0.5))
 
     # ---- device-resident workload ------------------------------------------------------
     dm = C.c_void_p()
-    _lib.check(lib.mag_devmesh_plate(ctx.handle, nx, ny, 2.0, 3.0, C.byref(dm)), "mag_devmesh_plate")
+    if weak:
+        _lib.check(lib.mag_devmesh_perforated(ctx.handle, nx, ny, 2.0, 64, 16, 3.0, C.byref(dm)), "mag_devmesh_perforated")
+    else:
+        _lib.check(lib.mag_devmesh_plate(ctx.handle, nx, ny, 2.0, 3.0, C.byref(dm)), "mag_devmesh_plate")
     view = _lib.MagMesh()
     _lib.check(lib.mag_devmesh_view(dm, C.byref(view)), "mag_devmesh_view")
     N, E = int(view.n_nodes), int(view.n_elems)
@@ -266,7 +274,7 @@ def run_ours(args):
     e2e = None
     barrier()
     if not args.no_e2e:
-        host = meshgen.plate(nx, ny)
+        host = meshgen.perforated_plate(nx, ny) if weak else meshgen.plate(nx, ny)
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         hx, hy = pin(host.x), pin(host.y)
         h0, h1, h2 = (pin(a.view(np.int32)) for a in (host.n0, host.n1, host.n2))
@@ -319,9 +327,10 @@ def run_ours(args):
         return
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(nx, ny),
+        "config": {"workload": ("perforated (pitch 64h, radius 16h) " if weak else "") + workload_name(nx, ny)
+                               + (f"; {E} triangles after perforation" if weak else ""),
                    "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: contiguous row blocks, P2P halo stores fused "
                                   f"into the CG update kernel, dot products allreduced "
                                   f"{'by NCCL' if args.allreduce else 'through peer-memory mailboxes inside the CG kernels'}",

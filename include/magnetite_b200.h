@@ -173,6 +173,12 @@ int mag_system_spmv_bench(mag_system *sys, int format, int reps, float *ms_per_s
 typedef struct mag_devmesh mag_devmesh;
 int mag_devmesh_plate(mag_ctx *ctx, uint32_t nx, uint32_t ny, double h, double ux_right,
                       mag_devmesh **out);
+/* Plate(nx,ny,h) minus the cells whose centre lies within radius*h of the lattice points
+ * ((k+0.5)*pitch*h, (l+0.5)*pitch*h); unreferenced nodes dropped, survivors renumbered row-major. */
+int mag_devmesh_perforated(mag_ctx *ctx, uint32_t nx, uint32_t ny, double h, uint32_t pitch,
+                           uint32_t radius, double ux_right, mag_devmesh **out);
+int mag_devmesh_download(const mag_devmesh *dm, double *x, double *y, uint32_t *n0, uint32_t *n1,
+                         uint32_t *n2, double *ux, double *uy, double *fx, double *fy, uint8_t *known);
 int mag_devmesh_view(const mag_devmesh *dm, mag_mesh *view);
 void mag_devmesh_free(mag_devmesh *dm);
 

@@ -93,6 +93,9 @@ _SIGNATURES = {
     "mag_system_spmv": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "mag_system_spmv_bench": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
     "mag_devmesh_plate": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.POINTER(_vp)]),
+    "mag_devmesh_perforated": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_double, C.c_uint32, C.c_uint32, C.c_double,
+                                         C.POINTER(_vp)]),
+    "mag_devmesh_download": (C.c_int, [_vp] + [_vp] * 10),
     "mag_devmesh_view": (C.c_int, [_vp, C.POINTER(MagMesh)]),
     "mag_devmesh_free": (None, [_vp]),
     "mag_comm_unique_id": (C.c_int, [_vp]),

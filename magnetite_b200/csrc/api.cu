@@ -413,6 +413,58 @@ extern "C" int mag_devmesh_plate(mag_ctx *ctx, uint32_t nx, uint32_t ny, double 
     });
 }
 
+extern "C" int mag_devmesh_perforated(mag_ctx *ctx, uint32_t nx, uint32_t ny, double h, uint32_t pitch,
+                                      uint32_t radius, double ux_right, mag_devmesh **out) {
+    return guarded([&] {
+        if (!out || nx == 0 || ny == 0 || pitch == 0) fail(MAG_ERR_BAD_ARG, "bad argument");
+        *out = nullptr;
+        CallScope scope(ctx, nullptr);
+        std::unique_ptr<mag_devmesh> dm(new mag_devmesh);
+        dm->ctx = ctx;
+        const size_t Ng = (size_t)(nx + 1) * (ny + 1), Cg = (size_t)nx * ny;
+        if (Ng >= (1ull << 31)) fail(MAG_ERR_BAD_ARG, "grid too large");
+        const double P = (double)pitch * h, R = (double)radius * h;
+        DevBuf<uint32_t> cell_pos(ctx, Cg + 1), node_pos(ctx, Ng + 1);
+        MAG_LAUNCH(ctx, perforated_flags_kernel, cdiv(Ng, 256), 256, 0, nx, ny, h, P, R * R, cell_pos.p, node_pos.p);
+        exclusive_scan_u32(ctx, cell_pos.p, Cg, cell_pos.p, Cg + 1);
+        exclusive_scan_u32(ctx, node_pos.p, Ng, node_pos.p, Ng + 1);
+        const size_t N = read_u32(ctx, node_pos.p + Ng), E = 2 * (size_t)read_u32(ctx, cell_pos.p + Cg);
+        dm->n_nodes = N; dm->n_elems = E;
+        dm->x.alloc(ctx, N); dm->y.alloc(ctx, N);
+        dm->ux.alloc(ctx, N); dm->uy.alloc(ctx, N); dm->fx.alloc(ctx, N); dm->fy.alloc(ctx, N);
+        dm->known.alloc(ctx, N);
+        dm->n0.alloc(ctx, E); dm->n1.alloc(ctx, E); dm->n2.alloc(ctx, E);
+        MAG_LAUNCH(ctx, perforated_nodes_kernel, cdiv(Ng, 256), 256, 0, nx, ny, h, ux_right,
+                   (const uint32_t *)node_pos.p, dm->x.p, dm->y.p, dm->ux.p, dm->uy.p, dm->fx.p, dm->fy.p, dm->known.p);
+        MAG_LAUNCH(ctx, perforated_elems_kernel, cdiv(Cg, 256), 256, 0, nx, ny, (const uint32_t *)cell_pos.p,
+                   (const uint32_t *)node_pos.p, dm->n0.p, dm->n1.p, dm->n2.p);
+        MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+        *out = dm.release();
+    });
+}
+
+// Copies a device mesh into caller-allocated host arrays (sizes from mag_devmesh_view).
+extern "C" int mag_devmesh_download(const mag_devmesh *dm, double *x, double *y, uint32_t *n0, uint32_t *n1,
+                                    uint32_t *n2, double *ux, double *uy, double *fx, double *fy, uint8_t *known) {
+    return guarded([&] {
+        if (!dm) fail(MAG_ERR_BAD_ARG, "null mesh");
+        mag_ctx *ctx = dm->ctx;
+        CallScope scope(ctx, nullptr);
+        const size_t N = dm->n_nodes, E = dm->n_elems;
+        if (x) copy_from_device(ctx, x, (const double *)dm->x.p, N, false);
+        if (y) copy_from_device(ctx, y, (const double *)dm->y.p, N, false);
+        if (n0) copy_from_device(ctx, n0, (const uint32_t *)dm->n0.p, E, false);
+        if (n1) copy_from_device(ctx, n1, (const uint32_t *)dm->n1.p, E, false);
+        if (n2) copy_from_device(ctx, n2, (const uint32_t *)dm->n2.p, E, false);
+        if (ux) copy_from_device(ctx, ux, (const double *)dm->ux.p, N, false);
+        if (uy) copy_from_device(ctx, uy, (const double *)dm->uy.p, N, false);
+        if (fx) copy_from_device(ctx, fx, (const double *)dm->fx.p, N, false);
+        if (fy) copy_from_device(ctx, fy, (const double *)dm->fy.p, N, false);
+        if (known) copy_from_device(ctx, known, (const uint8_t *)dm->known.p, N, false);
+        MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
 extern "C" int mag_devmesh_view(const mag_devmesh *dm, mag_mesh *v) {
     return guarded([&] {
         if (!dm || !v) fail(MAG_ERR_BAD_ARG, "null argument");

@@ -360,3 +360,21 @@ def test_cpp_host_layer_end_to_end(ctx, tmp_path):
     post_processor.csv_output(elements, nodes, str(tmp_path / "n_py.csv"), str(tmp_path / "e_py.csv"), quiet=True)
     assert (tmp_path / "n_cpp.csv").read_bytes() == (tmp_path / "n_py.csv").read_bytes()
     assert (tmp_path / "e_cpp.csv").read_bytes() == (tmp_path / "e_py.csv").read_bytes()
+
+
+def test_device_perforated_generator_matches_host(ctx):
+    import ctypes as C
+    lib = _lib.load()
+    dm = C.c_void_p()
+    _lib.check(lib.mag_devmesh_perforated(ctx.handle, 150, 70, 2.0, 32, 8, 3.0, C.byref(dm)), "perforated")
+    view = _lib.MagMesh()
+    _lib.check(lib.mag_devmesh_view(dm, C.byref(view)), "view")
+    host = meshgen.perforated_plate(150, 70, 2.0, pitch=32, radius=8).normalised()
+    assert (view.n_nodes, view.n_elems) == (host.n_nodes, host.n_elems) and host.n_elems < 2 * 150 * 70
+    N, E = host.n_nodes, host.n_elems
+    d = MeshSoA(np.empty(N), np.empty(N), np.empty(E, np.uint32), np.empty(E, np.uint32), np.empty(E, np.uint32),
+                np.empty(N), np.empty(N), np.empty(N), np.empty(N), np.empty(N, np.uint8))
+    _lib.check(lib.mag_devmesh_download(dm, *(_lib.ptr(a) for a in (d.x, d.y, d.n0, d.n1, d.n2, d.ux, d.uy, d.fx, d.fy, d.known))), "download")
+    for k in ("x", "y", "n0", "n1", "n2", "ux", "uy", "fx", "fy", "known"):
+        assert np.array_equal(getattr(d, k), getattr(host, k)), k
+    lib.mag_devmesh_free(dm)
