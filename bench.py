@@ -62,6 +62,20 @@ def workload_name(nx, ny):
            f"{2 * (nx + 1) * (ny + 1)} DOF, h=2, E=69e9, nu=0.33, t=0.5, left edge clamped, right edge ux=3"
 
 
+def ncu_traffic(nx, ny, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the SpMV kernel from the committed
+    ncu --set full capture of this workload (profiles/), or None when there is no capture for it."""
+    try:
+        cands = sorted((ROOT / "profiles").glob("r*_spmv_traffic.json"))
+        for path in reversed(cands):
+            for e in json.loads(path.read_text())["entries"]:
+                if (e["nx"], e["ny"], e["n_gpus"]) == (nx, ny, world):
+                    return int(e["dram_bytes_read"]) + int(e["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -148,6 +162,17 @@ def run_reference(args):
         v, dt, st = cpu_sample(nx, ny)
         vals.append(v); secs.append(dt)
     value = statistics.mean(vals)
+    # the reference's own data structures (dense (2N)^2 + dense partition + dense->CSR scan, plain CG to
+    # an absolute 1e-4) at a size they can hold: the README's linkedin case is ~7 k DOF
+    from magnetite_b200 import meshgen
+    from oracle import oracle as O
+    dmesh = meshgen.plate(80, 40)
+    t0 = time.perf_counter()
+    dres = O.run(O.Mesh(dmesh), meshgen.EXAMPLE_MATERIAL, O.cg_options(), dense=True)
+    ddt = time.perf_counter() - t0
+    dense = {"workload": "plate 80x40 cells (6400 triangles, 6642 DOF), the reference's dense algorithm and CG stopping rule",
+             "seconds": ddt, "melem_s": dmesh.n_elems / ddt / 1e6, "cg_iters": dres["stats"]["iters"],
+             "seconds_partition_and_dense_to_csr": dres["stats"]["t_part"], "seconds_cg": dres["stats"]["t_solve"]}
     sample = (f"plate {nx}x{ny} cells ({2 * nx * ny} triangles) solved completely per step by the oracle port "
               f"(reference arithmetic, CSR storage, Jacobi-PCG to 1e-9, {st['iters']} iterations); the 16M-DOF "
               f"workload needs ~{args.nx / nx:.0f}x more CG iterations per element, so this favours the CPU")
@@ -157,7 +182,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.nx, args.ny), "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                         "host_cores_available": os.cpu_count()},
+                         "host_cores_available": os.cpu_count(), "faithful_dense": dense},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -264,7 +289,8 @@ def run_ours(args):
     ms_iter = ms_solve / max(int(last.iters), 1)
     roofline = {"bound": "hbm", "kernel": "pcg_spmv_kernel (SELL-32 SpMV + fused p.q)", "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "algorithmic_bytes_per_launch": int(nbytes.value),
+                "traffic": None if weak else ncu_traffic(nx, ny, world),
+                "algorithmic_bytes_per_launch": int(nbytes.value),
                 "csr_equivalent_bytes": csr_bytes, "ms_per_launch": ms_spmv.value,
                 "pcg_iteration": {"bytes": iter_bytes, "ms": ms_iter,
                                   "achieved": iter_bytes / (ms_iter * 1e-3) / 1e9,
