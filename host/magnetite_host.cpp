@@ -28,6 +28,9 @@ namespace {
 struct Ctx {                       // RAII around mag_ctx
     mag_ctx *h = nullptr;
     explicit Ctx(int device) {
+        if (mag_abi_version() != MAG_ABI_VERSION)      // struct layouts differ: refuse instead of corrupting the stack
+            throw MagnetiteError(MagnetiteError::Kind::Solver, "libmagnetite_b200.so ABI version " +
+                                 std::to_string(mag_abi_version()) + " != header version " + std::to_string(MAG_ABI_VERSION));
         const int rc = mag_ctx_create(&h, device);
         if (rc != MAG_OK) throw MagnetiteError(MagnetiteError::Kind::Solver, mag_last_error(), rc);
     }

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MAG_ABI_VERSION 1
+#define MAG_ABI_VERSION 2   /* 2: mag_options grew coarse_aggregates; mag_stats grew prof[] */
 
 /* src/solver.rs:17-19 */
 #define MAG_DOF 2
@@ -80,7 +80,7 @@ typedef struct {
     double rel_tol;          /* stop at ||r||_2 <= rel_tol*||b||_2   (default 1e-9)   */
     double abs_tol;          /* compat target cost                   (default 1e-4)   */
     uint64_t max_iter;       /* default 1e7                                            */
-    int32_t precond;         /* 0 none, 1 Jacobi (default)                             */
+    int32_t precond;         /* 0 none, 1 Jacobi (default), 2 Jacobi + aggregation coarse space */
     int32_t compat;          /* 1: reference semantics — plain CG, x0=0, absolute cost */
     int32_t cost_kind;       /* compat cost: 0 = ||r||_2 (default), 1 = r.r            */
     int32_t drop_exact_zeros;/* 1 (default): K_ff keeps k != 0.0 only (solver.rs:132)  */
@@ -88,6 +88,8 @@ typedef struct {
     int32_t spmv_format;     /* 0 auto, 1 scalar CSR, 2 SELL-32                        */
     int32_t want_sigma;      /* also return sx,sy,txy per element                      */
     int32_t allreduce;       /* multi-GPU dot products: 0 peer-memory mailbox (default), 1 NCCL  */
+    int32_t coarse_aggregates; /* precond 2: number of aggregates (0 = auto, at most 2048)       */
+    int32_t reserved;
     void *stream;            /* cudaStream_t to run on, or NULL for the ctx's own      */
 } mag_options;
 

@@ -16,6 +16,7 @@ from .error import MagnetiteError
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libmagnetite_b200.so"
 
+ABI_VERSION = 2
 MAG_OK = 0
 MAG_ERR_CUDA, MAG_ERR_OOM, MAG_ERR_BAD_BC, MAG_ERR_BAD_INDEX = -1, -2, -3, -4
 MAG_ERR_INDEFINITE, MAG_ERR_NOT_CONVERGED, MAG_ERR_NCCL, MAG_ERR_BAD_ARG = -5, -6, -7, -8
@@ -43,6 +44,7 @@ class MagOptions(C.Structure):
                 ("precond", C.c_int32), ("compat", C.c_int32), ("cost_kind", C.c_int32),
                 ("drop_exact_zeros", C.c_int32), ("check_every", C.c_int32),
                 ("spmv_format", C.c_int32), ("want_sigma", C.c_int32), ("allreduce", C.c_int32),
+                ("coarse_aggregates", C.c_int32), ("reserved", C.c_int32),
                 ("stream", C.c_void_p)]
 
 
@@ -142,6 +144,8 @@ def load():
         fn = getattr(lib, name)          # AttributeError here = header/library drift
         fn.restype = res
         fn.argtypes = args
+    if lib.mag_abi_version() != ABI_VERSION:
+        raise MagnetiteError.Solver(f"{path} has ABI version {lib.mag_abi_version()}, this binding expects {ABI_VERSION}: rebuild")
     _lib = lib
     return lib
 

@@ -48,6 +48,7 @@ namespace mag {
 struct PcgScalars {
     double pair[2][2];   // pair[parity] = {r.z, r.r} entering an iteration of that parity (global sums)
     double pq;           // global p.q
+    double wy;           // two-level preconditioner: (P^T r).(Ac^-1 P^T r), the coarse part of r.z
     double loc_pair[2];  // this rank's partial sums (send buffers of the NCCL fallback)
     double loc_pq;
     double thr2;         // stop when r.r <= thr2
@@ -285,12 +286,23 @@ pcg_update_xr_kernel(double *__restrict__ x, double *__restrict__ r, const doubl
     if (grid_is_last_cta()) prof_end(sc, 4);
 }
 
+// Two-level preconditioner as seen by the p-update: z = Dinv r + P y (coarse.cuh); mode == null: off.
+struct CoarseView {
+    const uint32_t *mode = nullptr;   // per global reduced row: 3*aggregate + axis
+    const double *rot = nullptr;      // rotation-mode coefficient
+    const double *y = nullptr;        // Ac^-1 P^T r
+    __device__ __forceinline__ double prolong(uint32_t gi) const {
+        const uint32_t m = mode[gi];
+        return __ldg(y + m) + rot[gi] * __ldg(y + (m - m % 3u) + 2u);
+    }
+};
+
 // ---- C ----------------------------------------------------------------------------------
 // Rows [ext_lo, ext_hi) = owned block plus halo; halo rows take r from the halo buffer.
 __global__ void __launch_bounds__(256)
 pcg_update_p_kernel(double *__restrict__ p, const double *__restrict__ r,
                     const double *__restrict__ dinv, uint32_t ext_lo, uint32_t ext_hi, int step,
-                    HaloView halo, PeerLinks links, PcgScalars *sc) {
+                    HaloView halo, CoarseView cv, PeerLinks links, PcgScalars *sc) {
     if (sc->stop) return;
     prof_start(sc, 5);
     const int parity = step & 1;
@@ -300,6 +312,7 @@ pcg_update_p_kernel(double *__restrict__ p, const double *__restrict__ r,
         const double2 g = mailbox_gather(links, kMailPair, parity, seq, sc, 6);
         rz_new = g.x; rr = g.y;
     }
+    if (cv.mode) rz_new += sc->wy;          // r.z = r.Dinv r + (P^T r).(Ac^-1 P^T r)
     const double rz_old = sc->pair[parity][0], pq = sc->pq;
     const bool use_halo = halo.ll != nullptr && !(sc->tune & 1);
     // One thread moves the iteration on.  Nothing another CTA of this launch still reads is
@@ -322,7 +335,9 @@ pcg_update_p_kernel(double *__restrict__ p, const double *__restrict__ r,
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t gi = ext_lo + i;
         const double ri = (use_halo && halo.is_halo(gi)) ? ll_wait(halo.slot(gi), seq, sc) : r[gi];
-        p[gi] = fma(beta, p[gi], ri * dinv[gi]);
+        double z = ri * dinv[gi];
+        if (cv.mode) z += cv.prolong(gi);
+        p[gi] = fma(beta, p[gi], z);
     }
 }
 
@@ -366,18 +381,23 @@ pcg_init_kernel(double *__restrict__ x, double *__restrict__ r, double *__restri
 // p = Dinv r over owned + halo rows
 __global__ void __launch_bounds__(256)
 pcg_init_p_kernel(double *__restrict__ p, const double *__restrict__ r, const double *dinv,
-                  uint32_t ext_lo, uint32_t ext_hi, HaloView halo, PeerLinks links, PcgScalars *sc) {
+                  uint32_t ext_lo, uint32_t ext_hi, HaloView halo, CoarseView cv, PeerLinks links,
+                  PcgScalars *sc) {
     const uint32_t seq = ll_seq(sc, 0);
     if (links.n) {
         const double2 g = mailbox_gather(links, kMailInit, 0, seq, sc, -1);
-        if (blockIdx.x == 0 && threadIdx.x == 0) { sc->pair[0][0] = g.x; sc->pair[0][1] = g.y; }
+        if (blockIdx.x == 0 && threadIdx.x == 0) { sc->pair[0][0] = g.x + (cv.mode ? sc->wy : 0.0); sc->pair[0][1] = g.y; }
         __threadfence_system();        // acquire side of the Dinv halo
+    } else if (cv.mode && blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->pair[0][0] += sc->wy;
     }
     const uint32_t n = ext_hi - ext_lo;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t gi = ext_lo + i;
         const double ri = (halo.ll != nullptr && halo.is_halo(gi)) ? ll_wait(halo.slot(gi), seq, sc) : r[gi];
-        p[gi] = ri * __ldcv(dinv + gi);
+        double z = ri * __ldcv(dinv + gi);
+        if (cv.mode) z += cv.prolong(gi);
+        p[gi] = z;
     }
 }
 
@@ -391,6 +411,15 @@ __global__ void emulated_allreduce_kernel(ScalPtrs sp, int src_off, int dst_off,
     double s = 0.0;
     for (int r = 0; r < sp.n; ++r) s += reinterpret_cast<double *>(sp.p[r])[src_off + j];
     for (int r = 0; r < sp.n; ++r) reinterpret_cast<double *>(sp.p[r])[dst_off + j] = s;
+}
+
+struct VecPtrs { int n; double *p[16]; };
+__global__ void emulated_vec_allreduce_kernel(VecPtrs vp, size_t count) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (size_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < vp.n; ++r) s += vp.p[r][j];
+        for (int r = 0; r < vp.n; ++r) vp.p[r][j] = s;
+    }
 }
 
 // [min, max] of the column indices of a CSR block (halo extent of a rank)

@@ -150,7 +150,14 @@ constexpr size_t kOffLocPq = offsetof(PcgScalars, loc_pq) / sizeof(double);
 struct SolveMode {
     Reduce reduce = Reduce::kNone;
     int format = 2;
+    bool two_level = false;
 };
+
+inline CoarseView coarse_view(RankState &W, const SolveMode &m) {
+    CoarseView cv;
+    if (m.two_level) { cv.mode = W.S->coarse.mode.p; cv.rot = W.S->coarse.rot.p; cv.y = W.S->coarse.y.p; }
+    return cv;
+}
 
 inline double *scal_field(RankState &W, size_t off_doubles) {
     return reinterpret_cast<double *>(W.scal.p) + off_doubles;
@@ -184,6 +191,39 @@ static void reduce_scalars(mag_ctx *ctx, std::vector<RankState> &ranks, const So
     }
 }
 
+// Sum over ranks of a device vector each rank holds (in place).  No-op for a single rank.
+static void reduce_vector(mag_ctx *ctx, std::vector<RankState> &ranks, const SolveMode &m,
+                          const std::vector<double *> &vec, size_t count) {
+    if (ranks.size() > 1) {
+        VecPtrs vp;
+        vp.n = (int)ranks.size();
+        for (int r = 0; r < vp.n; ++r) vp.p[r] = vec[r];
+        MAG_LAUNCH(ctx, emulated_vec_allreduce_kernel, std::min(cdiv(count, 256), 1024u), 256, 0, vp, count);
+    } else if (ranks[0].S->nranks > 1) {
+        MAG_NCCL(ncclAllReduce(vec[0], vec[0], count, ncclDouble, ncclSum, ctx->comm->nccl, ctx->stream));
+    }
+    (void)m;
+}
+
+// w = P^T r (per rank) -> sum over ranks -> y = Ac^-1 w and wy = w.y (every rank, redundantly)
+static void enqueue_coarse_solve(mag_ctx *ctx, std::vector<RankState> &ranks, const SolveMode &m) {
+    std::vector<double *> ws;
+    for (RankState &W : ranks) {
+        CoarseSpace &C = W.S->coarse;
+        MAG_LAUNCH(ctx, coarse_restrict_kernel, C.n_agg, 128, 0, (const uint32_t *)C.agg_ptr.p,
+                   (const uint32_t *)C.perm.p, (const uint32_t *)C.mode.p, (const double *)C.rot.p,
+                   (const double *)W.r_ext, W.S->row_lo, C.w.p, (const PcgScalars *)W.scal.p);
+        ws.push_back(C.w.p);
+    }
+    reduce_vector(ctx, ranks, m, ws, ranks[0].S->coarse.nc);
+    for (RankState &W : ranks) {
+        CoarseSpace &C = W.S->coarse;
+        const unsigned grid = std::max(1u, std::min(cdiv((size_t)C.nc * 32, 256), (unsigned)ctx->sm_count * 8u));
+        MAG_LAUNCH(ctx, coarse_gemv_kernel, grid, 256, 0, (const double *)C.Ainv.p, (const double *)C.w.p, C.y.p,
+                   C.nc, C.partials.p, C.ticket.p, W.scal.p, scal_field(W, offsetof(PcgScalars, wy) / sizeof(double)));
+    }
+}
+
 static void enqueue_iteration(mag_ctx *ctx, std::vector<RankState> &ranks, int step, const SolveMode &m) {
     const int parity = step & 1;
     for (RankState &W : ranks) {
@@ -204,9 +244,91 @@ static void enqueue_iteration(mag_ctx *ctx, std::vector<RankState> &ranks, int s
                    (const double *)W.q.p, (const double *)W.dinv_ext, W.n, W.S->row_lo, step, W.S->push,
                    links_of(W, m), W.partials.p, W.scal.p, pair_target(W, m, parity ^ 1));
     reduce_scalars(ctx, ranks, m, kOffLocPair, kOffPair0 + 2 * (size_t)(parity ^ 1), 2);
+    if (m.two_level) enqueue_coarse_solve(ctx, ranks, m);
     for (RankState &W : ranks)
         MAG_LAUNCH(ctx, pcg_update_p_kernel, W.grid_ext, 256, 0, W.p_ext.p, (const double *)W.r_ext,
-                   (const double *)W.dinv_ext, W.S->ext_lo, W.S->ext_hi, step, W.halo, links_of(W, m), W.scal.p);
+                   (const double *)W.dinv_ext, W.S->ext_lo, W.S->ext_hi, step, W.halo, coarse_view(W, m),
+                   links_of(W, m), W.scal.p);
+}
+
+// Builds the aggregation coarse space of every rank's system (once per system).
+static void setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const SolveMode &m, const mag_options &opt) {
+    bool all_ready = true;
+    for (RankState &W : ranks) all_ready = all_ready && W.S->coarse.ready;
+    if (all_ready) return;
+    std::vector<double *> mats;
+    for (RankState &W : ranks) {
+        mag_system *S = W.S;
+        CoarseSpace &C = S->coarse;
+        const size_t N = S->n_nodes, n_dof = 2 * N;
+        // bounding box (global mesh: identical on every rank)
+        const unsigned bgrid = std::max(1u, std::min(cdiv(N, 256), 256u));
+        DevBuf<double> bb(ctx, (size_t)bgrid * 4);
+        MAG_LAUNCH(ctx, bbox_kernel, bgrid, 256, 0, (const double2 *)S->xy.p, N, bb.p);
+        std::vector<double> hb((size_t)bgrid * 4);
+        MAG_CUDA(cudaMemcpyAsync(hb.data(), bb.p, hb.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+        double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+        for (unsigned b = 0; b < bgrid; ++b) {
+            xmin = std::min(xmin, hb[4 * b]); xmax = std::max(xmax, hb[4 * b + 1]);
+            ymin = std::min(ymin, hb[4 * b + 2]); ymax = std::max(ymax, hb[4 * b + 3]);
+        }
+        const double Wd = std::max(xmax - xmin, 1e-300), Hd = std::max(ymax - ymin, 1e-300);
+        uint32_t target = opt.coarse_aggregates > 0 ? (uint32_t)opt.coarse_aggregates
+                                                    : (uint32_t)std::min<uint64_t>(2048, std::max<uint64_t>(4, S->n_free / 4096));
+        target = std::min(target, 2048u);
+        C.nbx = std::max(1u, (uint32_t)std::lround(std::sqrt((double)target * Wd / Hd)));
+        C.nby = std::max(1u, (uint32_t)std::lround((double)target / C.nbx));
+        C.n_agg = C.nbx * C.nby;
+        C.nc = 3 * C.n_agg;
+        C.x0 = xmin; C.y0 = ymin;
+        C.hx = Wd / C.nbx * (1.0 + 1e-12); C.hy = Hd / C.nby * (1.0 + 1e-12);
+        C.mode.alloc(ctx, ext_len(S)); C.rot.alloc(ctx, ext_len(S));
+        C.mode.zero(); C.rot.zero();
+        MAG_LAUNCH(ctx, coarse_colinfo_kernel, cdiv(n_dof, 256), 256, 0, (const double2 *)S->xy.p,
+                   (const uint8_t *)S->known.p, (const uint32_t *)S->colmap.p, n_dof, C.x0, C.y0, C.hx, C.hy,
+                   C.nbx, C.nby, C.mode.p, C.rot.p);
+        // local rows sorted by aggregate
+        const uint32_t n = S->Kff.n_rows;
+        C.perm.alloc(ctx, n);
+        C.agg_ptr.alloc(ctx, (size_t)C.n_agg + 1);
+        {
+            DevBuf<uint64_t> keys(ctx, n), keys_alt(ctx, n);
+            DevBuf<uint32_t> pay_alt(ctx, n);
+            if (n) {
+                MAG_LAUNCH(ctx, coarse_rowkeys_kernel, cdiv(n, 256), 256, 0, (const uint32_t *)C.mode.p, n, S->row_lo,
+                           keys.p, C.perm.p);
+                radix_sort_pairs(ctx, keys.p, C.perm.p, keys_alt.p, pay_alt.p, n, bits_for((uint64_t)C.n_agg + 1));
+            }
+            MAG_LAUNCH(ctx, coarse_segments_kernel, cdiv((size_t)C.n_agg + 1, 256), 256, 0, (const uint64_t *)keys.p, n,
+                       C.n_agg, C.agg_ptr.p);
+        }
+        // Galerkin product of the local rows
+        C.Ainv.alloc(ctx, (size_t)C.nc * C.nc);
+        C.Ainv.zero();
+        DevBuf<int> far(ctx, 1);
+        far.zero();
+        MAG_LAUNCH(ctx, coarse_galerkin_kernel, C.n_agg, 96, 0, (const uint32_t *)C.agg_ptr.p, (const uint32_t *)C.perm.p,
+                   (const uint32_t *)S->Kff.rowptr.p, (const int32_t *)S->Kff.col.p, (const double *)S->Kff.val.p,
+                   (const uint32_t *)C.mode.p, (const double *)C.rot.p, S->row_lo, C.nbx, C.nby, C.nc, C.Ainv.p, far.p);
+        int h_far = 0;
+        MAG_CUDA(cudaMemcpyAsync(&h_far, far.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (h_far) fail(MAG_ERR_BAD_ARG, "two-level preconditioner: an element spans non-adjacent aggregates "
+                                          "(%u x %u boxes are too small for this mesh); lower coarse_aggregates", C.nbx, C.nby);
+        C.w.alloc(ctx, C.nc); C.y.alloc(ctx, C.nc);
+        C.partials.alloc(ctx, 2 * (size_t)ctx->sm_count * 8);
+        C.ticket.alloc(ctx, 1);
+        C.ticket.zero();
+        mats.push_back(C.Ainv.p);
+    }
+    reduce_vector(ctx, ranks, m, mats, (size_t)ranks[0].S->coarse.nc * ranks[0].S->coarse.nc);
+    for (RankState &W : ranks) {
+        CoarseSpace &C = W.S->coarse;
+        MAG_LAUNCH(ctx, coarse_fix_diagonal_kernel, cdiv(C.nc, 256), 256, 0, C.Ainv.p, C.nc);
+        spd_inverse(ctx, C.Ainv.p, C.nc);
+        C.ready = true;
+    }
 }
 
 struct SolveOutcome {
@@ -222,6 +344,7 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
     else if (ranks[0].S->nranks > 1) mode.reduce = opt.allreduce == 1 ? Reduce::kNccl : Reduce::kMailbox;
     const bool compat = opt.compat != 0;
     const int jacobi = compat ? 0 : (opt.precond != 0);
+    mode.two_level = !compat && opt.precond == 2;
     int chunk = opt.check_every > 0 ? opt.check_every : 50;
     chunk += chunk & 1;   // iteration parity is baked into the graph: even chunk length
     SolveOutcome out;
@@ -229,6 +352,7 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
     PcgScalars &hs = out.hs;
     const uint32_t n_glob = ranks[0].S->n_free;
     if (n_glob == 0) { hs.stop = 1; return out; }
+    if (mode.two_level) setup_coarse(ctx, ranks, mode, opt);
 
     for (RankState &W : ranks) {
         PcgScalars z;
@@ -243,9 +367,11 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
                    W.S->push, links_of(W, mode), W.partials.p, W.scal.p, pair_target(W, mode, 0));
     // the reduction also orders the halo stores of r and Dinv before their readers
     reduce_scalars(ctx, ranks, mode, kOffLocPair, kOffPair0, 2);
+    if (mode.two_level) enqueue_coarse_solve(ctx, ranks, mode);
     for (RankState &W : ranks)
         MAG_LAUNCH(ctx, pcg_init_p_kernel, W.grid_ext, 256, 0, W.p_ext.p, (const double *)W.r_ext,
-                   (const double *)W.dinv_ext, W.S->ext_lo, W.S->ext_hi, W.halo, links_of(W, mode), W.scal.p);
+                   (const double *)W.dinv_ext, W.S->ext_lo, W.S->ext_hi, W.halo, coarse_view(W, mode),
+                   links_of(W, mode), W.scal.p);
     MAG_CUDA(cudaMemcpyAsync(&hs, ranks[0].scal.p, sizeof hs, cudaMemcpyDeviceToHost, ctx->stream));
     MAG_CUDA(cudaStreamSynchronize(ctx->stream));
     const double bb = hs.pair[0][1];

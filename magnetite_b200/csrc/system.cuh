@@ -14,6 +14,7 @@
 
 #include "assembly.cuh"
 #include "bc.cuh"
+#include "coarse.cuh"
 #include "comm.cuh"
 #include "common.cuh"
 #include "element.cuh"
@@ -41,6 +42,7 @@ struct mag_system {
     // halo buffers other ranks store into (plain cudaMalloc: exported through CUDA IPC)
     double *shared_slab = nullptr;           // [ Dinv (global-indexed) | mailbox | halo buffer of r ]
     std::vector<void *> ipc_opened;
+    mag::CoarseSpace coarse;                 // two-level preconditioner (built on first use)
     mag::PushSegs push;
     mag::PeerLinks links;                    // peer mailboxes (production multi-rank only)
     unsigned long long solve_epoch = 0;

@@ -1,6 +1,6 @@
 //! Thin `extern "C"` binding of libmagnetite_b200.so plus a safe wrapper with the exact
 //! signature of the reference's `solver::run` (src/solver.rs:543-547), so `main.rs:64`
-//! only changes its `use`.  Mirrors include/magnetite_b200.h (ABI version 1).
+//! only changes its `use`.  Mirrors include/magnetite_b200.h (ABI version 2).
 //!
 //! UNVERIFIED: there is no Rust toolchain in the build image; this file has never been
 //! compiled.  The Python ctypes binding (magnetite_b200/_lib.py) exercises the same ABI.
@@ -47,6 +47,8 @@ pub mod sys {
         pub spmv_format: i32,
         pub want_sigma: i32,
         pub allreduce: i32,
+        pub coarse_aggregates: i32,
+        pub reserved: i32,
         pub stream: *mut c_void,
     }
     #[repr(C)]

@@ -351,6 +351,7 @@ def test_cpp_host_layer_end_to_end(ctx, tmp_path):
     from magnetite_b200 import post_processor
     root = Path(__file__).resolve().parent.parent
     exe = root / "host" / "plate_demo"
+    subprocess.run(["make", "-C", str(root / "host")], check=True, capture_output=True)   # header may have changed
     r = subprocess.run([str(exe), "12", "6", str(tmp_path / "n_cpp.csv"), str(tmp_path / "e_cpp.csv")],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
@@ -378,3 +379,43 @@ def test_device_perforated_generator_matches_host(ctx):
     for k in ("x", "y", "n0", "n1", "n2", "ux", "uy", "fx", "fy", "known"):
         assert np.array_equal(getattr(d, k), getattr(host, k)), k
     lib.mag_devmesh_free(dm)
+
+
+TWO_LEVEL_MESHES = {
+    "plate_120x60": lambda: meshgen.plate(120, 60),
+    "jitter_90x50": lambda: meshgen.jitter(meshgen.plate(90, 50)),
+    "perforated_128x64": lambda: meshgen.perforated_plate(128, 64, pitch=32, radius=8),
+}
+
+
+@pytest.mark.parametrize("name", list(TWO_LEVEL_MESHES))
+def test_two_level_preconditioner_matches_oracle(ctx, name):
+    """precond=2 (Jacobi + aggregation coarse space): same answer as the oracle,
+    far fewer iterations than Jacobi, bit-identical run to run, also over virtual ranks."""
+    mesh = TWO_LEVEL_MESHES[name]()
+    ref = O.run(O.Mesh(mesh), META, O.cg_options(), dense=False)
+    ur = np.concatenate([ref["ux"], ref["uy"]])
+    with solver.System(mesh, META, ctx) as S:
+        jac = S.solve(_lib.default_options(rel_tol=1e-13))
+        two = S.solve(_lib.default_options(rel_tol=1e-13, precond=2, coarse_aggregates=32))
+        again = S.solve(_lib.default_options(rel_tol=1e-13, precond=2, coarse_aggregates=32))
+    assert two.stats["converged"] == 1
+    assert rel_l2(np.concatenate([two.ux, two.uy]), ur) < 1e-9
+    assert np.abs(two.stress - ref["stress"]).max() / np.abs(ref["stress"]).max() < 1e-8
+    assert two.stats["iters"] < 0.6 * jac.stats["iters"], (two.stats["iters"], jac.stats["iters"])
+    assert again.ux.tobytes() == two.ux.tobytes() and again.stats["iters"] == two.stats["iters"]
+    vr = solver.virtual_rank_solve(mesh, META, 3, ctx, _lib.default_options(rel_tol=1e-13, precond=2, coarse_aggregates=32))
+    assert rel_l2(np.concatenate([vr.ux, vr.uy]), ur) < 1e-9
+    assert abs(int(vr.stats["iters"]) - int(two.stats["iters"])) <= max(3, two.stats["iters"] // 20)
+
+
+def test_two_level_on_examples_and_indefinite_meshes(ctx):
+    g = np.load(GOLDEN / "example_linkedin.npz")
+    mesh = golden_mesh(g)
+    meta = META.__class__(*g["material"])
+    two = solver.solve_soa(mesh, meta, ctx, _lib.default_options(rel_tol=1e-13, precond=2))
+    assert rel_l2(np.concatenate([two.ux, two.uy]), np.concatenate([g["ux"], g["uy"]])) < 1e-9
+    t = np.load(GOLDEN / "example_tensile.npz")            # all-clockwise mesh: negative definite
+    with pytest.raises(MagnetiteError) as ei:
+        solver.solve_soa(golden_mesh(t), META.__class__(*t["material"]), ctx, _lib.default_options(precond=2))
+    assert ei.value.code == _lib.MAG_ERR_INDEFINITE
