@@ -122,6 +122,8 @@ typedef struct {
      * 3 update_xr wait for the global p.q   4 update_xr duration  5 update_p.start - update_xr.end
      * 6 update_p wait for the global r.z    7 iterations timed                                  */
     double prof[8];
+    float ms_coarse_setup;             /* precond 2: building P, Ac and Ac^-1 (inside ms_solve, first solve only) */
+    uint32_t n_coarse;                 /* precond 2: coarse unknowns (3 per aggregate)                            */
 } mag_stats;
 
 typedef struct mag_ctx mag_ctx;        /* device + stream + memory pool + comm    */

@@ -334,6 +334,8 @@ static void setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
 struct SolveOutcome {
     PcgScalars hs;
     double bb = 0.0;
+    float ms_coarse_setup = 0.f;
+    uint32_t n_coarse = 0;
 };
 
 // Runs CG over `ranks` (size 1 in production).  All ranks see identical scalars.
@@ -352,7 +354,13 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
     PcgScalars &hs = out.hs;
     const uint32_t n_glob = ranks[0].S->n_free;
     if (n_glob == 0) { hs.stop = 1; return out; }
-    if (mode.two_level) setup_coarse(ctx, ranks, mode, opt);
+    if (mode.two_level) {
+        EventTimer t(ctx->stream);
+        t.start();
+        setup_coarse(ctx, ranks, mode, opt);
+        out.ms_coarse_setup = t.stop();
+        out.n_coarse = ranks[0].S->coarse.nc;
+    }
 
     for (RankState &W : ranks) {
         PcgScalars z;
@@ -453,6 +461,8 @@ static void fill_solve_stats(mag_stats &st, const SolveOutcome &o, uint32_t n_gl
     st.b_norm = std::sqrt(o.bb);
     st.final_residual = std::sqrt(hs.iter ? hs.pair[last][1] : o.bb);
     st.converged = (hs.stop == 1) || n_glob == 0;
+    st.ms_coarse_setup = o.ms_coarse_setup;
+    st.n_coarse = o.n_coarse;
     for (int i = 0; i < 8; ++i) st.prof[i] = hs.prof[7] > 0 && i < 7 ? hs.prof[i] / hs.prof[7] : hs.prof[i];
     st.negative_definite = hs.first_pq < 0.0;
 }

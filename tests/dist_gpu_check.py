@@ -18,9 +18,10 @@ def main():
     ctx = _lib.Context(local)
     mdist.init_comm(ctx)
     meta = meshgen.EXAMPLE_MATERIAL
-    cases = [(meshgen.jitter(meshgen.plate(96, 64)), 0), (meshgen.plate(300, 200), 0), (meshgen.plate(300, 200), 1)]
-    for mesh, allreduce in cases:              # allreduce 0: peer-memory mailbox, 1: NCCL
-        opt = _lib.default_options(rel_tol=1e-12, allreduce=allreduce)
+    cases = [(meshgen.jitter(meshgen.plate(96, 64)), 0, 1), (meshgen.plate(300, 200), 0, 1), (meshgen.plate(300, 200), 1, 1),
+             (meshgen.plate(300, 200), 0, 2), (meshgen.perforated_plate(256, 128, pitch=32, radius=8), 1, 2)]
+    for mesh, allreduce, precond in cases:     # allreduce 0: peer-memory mailbox, 1: NCCL; precond 2: two-level
+        opt = _lib.default_options(rel_tol=1e-12, allreduce=allreduce, precond=precond, coarse_aggregates=64 if precond == 2 else 0)
         sol = solver.solve_soa(mesh, meta, ctx, opt)            # comm-aware: this rank's row block
         sol2 = solver.solve_soa(mesh, meta, ctx, opt)
         assert sol.ux.tobytes() == sol2.ux.tobytes(), "not deterministic run to run"
@@ -32,7 +33,7 @@ def main():
             ferr = np.abs(np.concatenate([sol.fx - one.fx, sol.fy - one.fy])).max() / np.abs(one.fx).max()
             serr = np.abs(sol.stress - one.stress).max() / np.abs(one.stress).max()
             assert 0.1 < sol.stats["final_residual"] / one.stats["final_residual"] < 10.0   # same stopping point
-            print(f"rank0: {mesh.n_elems} elements, world {world}, allreduce {allreduce}: iters {sol.stats['iters']} vs {one.stats['iters']}, "
+            print(f"rank0: {mesh.n_elems} elements, world {world}, allreduce {allreduce}, precond {precond}: iters {sol.stats['iters']} vs {one.stats['iters']}, "
                   f"|du| {err:.2e}, |df| {ferr:.2e}, |ds| {serr:.2e}", flush=True)
             assert err < 1e-9 and ferr < 1e-7 and serr < 1e-8
             assert abs(int(sol.stats["iters"]) - int(one.stats["iters"])) <= 5
