@@ -383,7 +383,7 @@ def run_ours(args):
                                   f"into the CG update kernel, dot products allreduced "
                                   f"{'by NCCL' if args.allreduce else 'through peer-memory mailboxes inside the CG kernels'}",
                    "l2": "inputs larger than L2 (K_ff + vectors >> 126 MB), no flush needed",
-                   "solver": "Jacobi-PCG, rel_tol 1e-9, SELL-32 SpMV", "n_free": int(last.n_free),
+                   "solver": f"Jacobi-PCG, rel_tol 1e-9, SELL-32 SpMV with {int(last.sell_index_bits)}-bit column indices", "n_free": int(last.n_free),
                    "nnz": int(last.nnz), "nnz_structural": int(last.nnz_structural)},
         "metrics": {"assembly_melem_s": E / (ms_asm * 1e-3) / 1e6, "assembly_ms": ms_asm,
                     "pcg_time_to_solve_s": ms_solve * 1e-3, "pcg_iters": int(last.iters),

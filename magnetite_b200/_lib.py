@@ -64,7 +64,8 @@ class MagStats(C.Structure):
                 ("ms_solve", C.c_float), ("ms_post", C.c_float), ("ms_download", C.c_float),
                 ("ms_total", C.c_float), ("kernel_launches", C.c_uint64),
                 ("spmv_bytes", C.c_uint64), ("prof", C.c_double * 8),
-                ("ms_coarse_setup", C.c_float), ("n_coarse", C.c_uint32)]
+                ("ms_coarse_setup", C.c_float), ("n_coarse", C.c_uint32),
+                ("sell_index_bits", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self) -> dict:
         d = {name: getattr(self, name) for name, _ in self._fields_}

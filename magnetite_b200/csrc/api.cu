@@ -328,8 +328,12 @@ static void launch_spmv(mag_ctx *ctx, mag_system *S, int format, const double *x
     if (format == 1) {
         MAG_LAUNCH(ctx, spmv_csr_kernel, cdiv(A.n_rows, 256), 256, 0, (const uint32_t *)A.rowptr.p,
                    (const int32_t *)A.col.p, (const double *)A.val.p, x, y, A.n_rows);
+    } else if (L.narrow) {
+        MAG_LAUNCH(ctx, spmv_sell_kernel<int16_t>, sell_grid(ctx, L.n_slices), 256, 0,
+                   (const uint32_t *)L.slice_off.p, (const int16_t *)L.dcol.p, (const double *)L.val.p, x, y,
+                   L.n_rows, L.n_slices, L.row_lo);
     } else {
-        MAG_LAUNCH(ctx, spmv_sell_kernel, sell_grid(ctx, L.n_slices), 256, 0,
+        MAG_LAUNCH(ctx, spmv_sell_kernel<int32_t>, sell_grid(ctx, L.n_slices), 256, 0,
                    (const uint32_t *)L.slice_off.p, (const int32_t *)L.col.p, (const double *)L.val.p, x, y,
                    L.n_rows, L.n_slices, L.row_lo);
     }
@@ -367,8 +371,12 @@ extern "C" int mag_system_spmv_bench(mag_system *sys, int format, int reps, floa
         DevBuf<PcgScalars> scal(ctx, 1);
         scal.zero();
         auto once = [&] {
-            if (format == 2 && n)
-                MAG_LAUNCH(ctx, pcg_spmv_kernel, grid, 256, 0, (const uint32_t *)L.slice_off.p,
+            if (format == 2 && n && L.narrow)
+                MAG_LAUNCH(ctx, pcg_spmv_kernel<int16_t>, grid, 256, 0, (const uint32_t *)L.slice_off.p,
+                           (const int16_t *)L.dcol.p, (const double *)L.val.p, (const double *)dx.p, dy.p,
+                           L.n_rows, L.n_slices, L.row_lo, 0, PeerLinks{}, partials.p, scal.p, &scal.p->pq);
+            else if (format == 2 && n)
+                MAG_LAUNCH(ctx, pcg_spmv_kernel<int32_t>, grid, 256, 0, (const uint32_t *)L.slice_off.p,
                            (const int32_t *)L.col.p, (const double *)L.val.p, (const double *)dx.p, dy.p,
                            L.n_rows, L.n_slices, L.row_lo, 0, PeerLinks{}, partials.p, scal.p, &scal.p->pq);
             else
@@ -381,7 +389,7 @@ extern "C" int mag_system_spmv_bench(mag_system *sys, int format, int reps, floa
         *ms_per_spmv = t.stop() / (float)reps;
         if (algorithmic_bytes) {
             if (format == 1) *algorithmic_bytes = sys->stats.spmv_bytes;
-            else *algorithmic_bytes = sys->sell.entries * 12ull + (uint64_t)n * 16ull +
+            else *algorithmic_bytes = sys->sell.entries * 8ull + sys->sell.index_bytes() + (uint64_t)n * 16ull +
                                       ((uint64_t)sys->sell.n_slices + 1) * 4ull;
         }
     });

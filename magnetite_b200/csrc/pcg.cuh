@@ -199,8 +199,9 @@ __device__ __forceinline__ void push_dinv(const PushSegs &ps, uint32_t gi, doubl
 }
 
 // ---- A ----------------------------------------------------------------------------------
+template <class IDX>
 __global__ void __launch_bounds__(256, 6)
-pcg_spmv_kernel(const uint32_t *__restrict__ slice_off, const int32_t *__restrict__ scol,
+pcg_spmv_kernel(const uint32_t *__restrict__ slice_off, const IDX *__restrict__ scol,
                 const double *__restrict__ sval, const double *__restrict__ p,
                 double *__restrict__ q, uint32_t n_rows, uint32_t n_slices, uint32_t row_lo,
                 int step, PeerLinks links, double *__restrict__ partials, PcgScalars *sc,
@@ -208,7 +209,7 @@ pcg_spmv_kernel(const uint32_t *__restrict__ slice_off, const int32_t *__restric
     if (sc->stop) return;
     prof_start(sc, 0);
     const int parity = step & 1;
-    double v[1] = {sell_rows<true>(slice_off, scol, sval, p, q, n_rows, n_slices, row_lo)};
+    double v[1] = {sell_rows<true, IDX>(slice_off, scol, sval, p, q, n_rows, n_slices, row_lo)};
     double tot[1] = {0.0};
     const bool last = grid_sum_256<1>(v, partials, &sc->ticket_a, tot);
     if (links.n) {

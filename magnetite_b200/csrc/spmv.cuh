@@ -30,9 +30,12 @@ struct CsrMatrix {                 // local rows [row_lo, row_lo+n_rows) x globa
 struct SellMatrix {
     uint32_t n_rows = 0, n_slices = 0, row_lo = 0;
     uint64_t entries = 0;          // padded entries (multiple of 32)
+    bool narrow = false;           // columns stored as int16 offsets from the row (band < 32768)
     DevBuf<uint32_t> slice_off;    // n_slices+1, in units of 32 entries
-    DevBuf<int32_t> col;
+    DevBuf<int32_t> col;           // wide index stream   (narrow == false)
+    DevBuf<int16_t> dcol;          // narrow index stream (narrow == true): col = global row + dcol
     DevBuf<double> val;
+    uint64_t index_bytes() const { return entries * (narrow ? 2ull : 4ull); }
 };
 
 // ---- CSR -> SELL-32 --------------------------------------------------------
@@ -46,10 +49,24 @@ __global__ void sell_width_kernel(const uint32_t *__restrict__ rowptr, uint32_t 
     if ((threadIdx.x & 31) == 0 && s < n_slices) width[s] = len;
 }
 
+// largest |col - global row| of a CSR block: decides whether 16-bit column offsets suffice
+__global__ void band_width_kernel(const uint32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                  uint32_t n_rows, uint32_t row_lo, int *__restrict__ band) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = 0;
+    if (row < n_rows)
+        for (uint32_t p = rowptr[row]; p < rowptr[row + 1]; ++p) b = max(b, abs(col[p] - (int)(row_lo + row)));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, off));
+    if ((threadIdx.x & 31) == 0 && b) atomicMax(band, b);
+}
+
+template <class IDX>
 __global__ void sell_fill_kernel(const uint32_t *__restrict__ rowptr, const int32_t *__restrict__ ccol,
                                  const double *__restrict__ cval, uint32_t n_rows, uint32_t row_lo,
-                                 const uint32_t *__restrict__ slice_off, int32_t *__restrict__ scol,
+                                 const uint32_t *__restrict__ slice_off, IDX *__restrict__ scol,
                                  double *__restrict__ sval) {
+    constexpr bool kNarrow = sizeof(IDX) == 2;
     const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t s = row >> 5, lane = threadIdx.x & 31;
     // whole warps stay together: a slice is written by the warp that owns it
@@ -59,16 +76,17 @@ __global__ void sell_fill_kernel(const uint32_t *__restrict__ rowptr, const int3
     const size_t base = (size_t)slice_off[s] * 32 + lane;
     const uint32_t p0 = (row < n_rows) ? rowptr[row] : 0u;
     const uint32_t len = (row < n_rows) ? rowptr[row + 1] - p0 : 0u;
-    // padding multiplies 0.0 by x at a column that is always valid and cached
-    const int32_t pad_col = (int32_t)(row_lo + (row < n_rows ? row : n_rows - 1));
+    // padding multiplies 0.0 by x at the row's own column (x is padded by 32 finite entries)
+    const int32_t grow = (int32_t)(row_lo + row);
     for (uint32_t k = 0; k < w; ++k) {
         const bool real = k < len;
-        scol[base + (size_t)k * 32] = real ? ccol[p0 + k] : pad_col;
+        const int32_t c = real ? ccol[p0 + k] : grow;
+        scol[base + (size_t)k * 32] = kNarrow ? (IDX)(c - grow) : (IDX)c;
         sval[base + (size_t)k * 32] = real ? cval[p0 + k] : 0.0;
     }
 }
 
-inline void build_sell(mag_ctx *ctx, const CsrMatrix &A, SellMatrix &S) {
+inline void build_sell(mag_ctx *ctx, const CsrMatrix &A, SellMatrix &S, bool allow_narrow = true) {
     S.n_rows = A.n_rows; S.row_lo = A.row_lo;
     S.n_slices = (A.n_rows + 31) / 32;
     S.slice_off.alloc(ctx, (size_t)S.n_slices + 1);
@@ -82,11 +100,28 @@ inline void build_sell(mag_ctx *ctx, const CsrMatrix &A, SellMatrix &S) {
                              cudaMemcpyDeviceToHost, ctx->stream));
     MAG_CUDA(cudaStreamSynchronize(ctx->stream));
     S.entries = (uint64_t)groups * 32;
-    S.col.alloc(ctx, S.entries);
+    int h_band = 0;
+    {
+        DevBuf<int> band(ctx, 1);
+        band.zero();
+        MAG_LAUNCH(ctx, band_width_kernel, blocks, 256, 0, (const uint32_t *)A.rowptr.p, (const int32_t *)A.col.p,
+                   A.n_rows, A.row_lo, band.p);
+        MAG_CUDA(cudaMemcpyAsync(&h_band, band.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    S.narrow = allow_narrow && h_band < 32768;
     S.val.alloc(ctx, S.entries);
-    MAG_LAUNCH(ctx, sell_fill_kernel, blocks, 256, 0, (const uint32_t *)A.rowptr.p,
-               (const int32_t *)A.col.p, (const double *)A.val.p, A.n_rows, A.row_lo,
-               (const uint32_t *)S.slice_off.p, S.col.p, S.val.p);
+    if (S.narrow) {
+        S.dcol.alloc(ctx, S.entries);
+        MAG_LAUNCH(ctx, sell_fill_kernel<int16_t>, blocks, 256, 0, (const uint32_t *)A.rowptr.p,
+                   (const int32_t *)A.col.p, (const double *)A.val.p, A.n_rows, A.row_lo,
+                   (const uint32_t *)S.slice_off.p, S.dcol.p, S.val.p);
+    } else {
+        S.col.alloc(ctx, S.entries);
+        MAG_LAUNCH(ctx, sell_fill_kernel<int32_t>, blocks, 256, 0, (const uint32_t *)A.rowptr.p,
+                   (const int32_t *)A.col.p, (const double *)A.val.p, A.n_rows, A.row_lo,
+                   (const uint32_t *)S.slice_off.p, S.col.p, S.val.p);
+    }
 }
 
 // ---- deterministic grid-wide sums ------------------------------------------
@@ -157,33 +192,36 @@ __device__ __forceinline__ bool grid_sum_256(double (&v)[NV], double *__restrict
 // ---- SELL-32 SpMV ----------------------------------------------------------
 // One warp per slice, grid-stride over slices.  x is indexed by global column;
 // y by local row.  If DOT, also accumulates sum_i x[row_lo+i]*y[i].
-template <bool DOT>
+template <bool DOT, class IDX>
 __device__ __forceinline__ double sell_rows(const uint32_t *__restrict__ slice_off,
-                                            const int32_t *__restrict__ scol,
+                                            const IDX *__restrict__ scol,
                                             const double *__restrict__ sval,
                                             const double *__restrict__ x, double *__restrict__ y,
                                             uint32_t n_rows, uint32_t n_slices, uint32_t row_lo) {
+    constexpr bool kNarrow = sizeof(IDX) == 2;
     const int lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     double dot = 0.0;
     for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slices; s += warps) {
         const uint32_t o0 = __ldg(&slice_off[s]), o1 = __ldg(&slice_off[s + 1]);
         const double *v = sval + (size_t)o0 * 32 + lane;
-        const int32_t *c = scol + (size_t)o0 * 32 + lane;
+        const IDX *c = scol + (size_t)o0 * 32 + lane;
         const uint32_t w = o1 - o0;
+        const uint32_t row = s * 32 + lane;
+        // narrow: the stream holds offsets from the row's own (global) column
+        const double *xb = kNarrow ? x + (row_lo + row) : x;
         double acc0 = 0.0, acc1 = 0.0;
         uint32_t k = 0;
         for (; k + 4 <= w; k += 4) {
             const double a0 = __ldcs(v + (size_t)(k + 0) * 32), a1 = __ldcs(v + (size_t)(k + 1) * 32);
             const double a2 = __ldcs(v + (size_t)(k + 2) * 32), a3 = __ldcs(v + (size_t)(k + 3) * 32);
-            const int32_t c0 = __ldcs(c + (size_t)(k + 0) * 32), c1 = __ldcs(c + (size_t)(k + 1) * 32);
-            const int32_t c2 = __ldcs(c + (size_t)(k + 2) * 32), c3 = __ldcs(c + (size_t)(k + 3) * 32);
-            const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+            const int c0 = __ldcs(c + (size_t)(k + 0) * 32), c1 = __ldcs(c + (size_t)(k + 1) * 32);
+            const int c2 = __ldcs(c + (size_t)(k + 2) * 32), c3 = __ldcs(c + (size_t)(k + 3) * 32);
+            const double x0 = __ldg(xb + c0), x1 = __ldg(xb + c1), x2 = __ldg(xb + c2), x3 = __ldg(xb + c3);
             acc0 = fma(a0, x0, acc0); acc1 = fma(a1, x1, acc1);
             acc0 = fma(a2, x2, acc0); acc1 = fma(a3, x3, acc1);
         }
-        for (; k < w; ++k) acc0 = fma(__ldcs(v + (size_t)k * 32), __ldg(x + __ldcs(c + (size_t)k * 32)), acc0);
-        const uint32_t row = s * 32 + lane;
+        for (; k < w; ++k) acc0 = fma(__ldcs(v + (size_t)k * 32), __ldg(xb + (int)__ldcs(c + (size_t)k * 32)), acc0);
         if (row < n_rows) {
             const double yi = acc0 + acc1;
             y[row] = yi;
@@ -193,11 +231,12 @@ __device__ __forceinline__ double sell_rows(const uint32_t *__restrict__ slice_o
     return dot;
 }
 
+template <class IDX>
 __global__ void __launch_bounds__(256, 6)
-spmv_sell_kernel(const uint32_t *__restrict__ slice_off, const int32_t *__restrict__ scol,
+spmv_sell_kernel(const uint32_t *__restrict__ slice_off, const IDX *__restrict__ scol,
                  const double *__restrict__ sval, const double *__restrict__ x,
                  double *__restrict__ y, uint32_t n_rows, uint32_t n_slices, uint32_t row_lo) {
-    (void)sell_rows<false>(slice_off, scol, sval, x, y, n_rows, n_slices, row_lo);
+    (void)sell_rows<false, IDX>(slice_off, scol, sval, x, y, n_rows, n_slices, row_lo);
 }
 
 // ---- scalar CSR SpMV (thread per row; parity path and format comparison) ---

@@ -307,8 +307,9 @@ static void assemble_impl(mag_ctx *ctx, const mag_mesh *m, const mag_material *m
 
     // ---- solver format -------------------------------------------------------------
     phase.start();
-    build_sell(ctx, A, S->sell);
+    build_sell(ctx, A, S->sell, !(opt && opt->spmv_format == 3));
     st.sell_entries = S->sell.entries;
+    st.sell_index_bits = S->sell.narrow ? 16 : 32;
     st.ms_format = phase.stop();
     st.spmv_bytes = A.nnz * 12ull + (uint64_t)n_rows * 16ull + ((uint64_t)n_rows + 1) * 4ull;
     st.ms_total = total.stop();

@@ -419,3 +419,19 @@ def test_two_level_on_examples_and_indefinite_meshes(ctx):
     with pytest.raises(MagnetiteError) as ei:
         solver.solve_soa(golden_mesh(t), META.__class__(*t["material"]), ctx, _lib.default_options(precond=2))
     assert ei.value.code == _lib.MAG_ERR_INDEFINITE
+
+
+def test_narrow_and_wide_sell_index_streams_agree(ctx):
+    """16-bit column offsets (banded numbering) and 32-bit absolute columns carry the same matrix:
+    identical SpMV results and identical CG iterates; unstructured numbering falls back to 32 bits."""
+    mesh = meshgen.jitter(meshgen.plate(150, 40))
+    x = np.random.default_rng(5).normal(size=2 * mesh.n_nodes)
+    with solver.System(mesh, META, ctx) as N, solver.System(mesh, META, ctx, options=_lib.default_options(spmv_format=3)) as W:
+        assert N.assemble_stats["sell_index_bits"] == 16 and W.assemble_stats["sell_index_bits"] == 32
+        xs = x[: N.n_free]
+        assert np.array_equal(N.spmv(xs, fmt=2), W.spmv(xs, fmt=2))
+        a, b = N.solve(_lib.default_options()), W.solve(_lib.default_options(spmv_format=3))
+        assert a.ux.tobytes() == b.ux.tobytes() and a.stats["iters"] == b.stats["iters"]
+    g = np.load(GOLDEN / "example_cover.npz")                      # Delaunay numbering: wide band
+    with solver.System(golden_mesh(g), META.__class__(*g["material"]), ctx) as S:
+        assert S.assemble_stats["sell_index_bits"] == 32
