@@ -330,7 +330,7 @@ static void launch_spmv(mag_ctx *ctx, mag_system *S, int format, const double *x
                    (const int32_t *)A.col.p, (const double *)A.val.p, x, y, A.n_rows);
     } else if (L.narrow) {
         MAG_LAUNCH(ctx, spmv_sell_kernel<int16_t>, sell_grid(ctx, L.n_slices), 256, 0,
-                   (const uint32_t *)L.slice_off.p, (const int16_t *)L.dcol.p, (const double *)L.val.p, x, y,
+                   (const uint32_t *)L.slice_off.p, (const int16_t *)L.pcol.p, (const double *)L.val.p, x, y,
                    L.n_rows, L.n_slices, L.row_lo);
     } else {
         MAG_LAUNCH(ctx, spmv_sell_kernel<int32_t>, sell_grid(ctx, L.n_slices), 256, 0,
@@ -373,7 +373,7 @@ extern "C" int mag_system_spmv_bench(mag_system *sys, int format, int reps, floa
         auto once = [&] {
             if (format == 2 && n && L.narrow)
                 MAG_LAUNCH(ctx, pcg_spmv_kernel<int16_t>, grid, 256, 0, (const uint32_t *)L.slice_off.p,
-                           (const int16_t *)L.dcol.p, (const double *)L.val.p, (const double *)dx.p, dy.p,
+                           (const int16_t *)L.pcol.p, (const double *)L.val.p, (const double *)dx.p, dy.p,
                            L.n_rows, L.n_slices, L.row_lo, 0, PeerLinks{}, partials.p, scal.p, &scal.p->pq);
             else if (format == 2 && n)
                 MAG_LAUNCH(ctx, pcg_spmv_kernel<int32_t>, grid, 256, 0, (const uint32_t *)L.slice_off.p,

@@ -235,7 +235,7 @@ static void enqueue_iteration(mag_ctx *ctx, std::vector<RankState> &ranks, int s
                        W.n, A.row_lo, step, links_of(W, m), W.partials.p, W.scal.p, pq_target(W, m));
         else if (L.narrow)
             MAG_LAUNCH(ctx, pcg_spmv_kernel<int16_t>, W.grid_spmv, 256, 0, (const uint32_t *)L.slice_off.p,
-                       (const int16_t *)L.dcol.p, (const double *)L.val.p, (const double *)W.p_ext.p, W.q.p,
+                       (const int16_t *)L.pcol.p, (const double *)L.val.p, (const double *)W.p_ext.p, W.q.p,
                        W.n, L.n_slices, L.row_lo, step, links_of(W, m), W.partials.p, W.scal.p, pq_target(W, m));
         else
             MAG_LAUNCH(ctx, pcg_spmv_kernel<int32_t>, W.grid_spmv, 256, 0, (const uint32_t *)L.slice_off.p,

@@ -33,19 +33,20 @@ struct SellMatrix {
     bool narrow = false;           // columns stored as int16 offsets from the row (band < 32768)
     DevBuf<uint32_t> slice_off;    // n_slices+1, in units of 32 entries
     DevBuf<int32_t> col;           // wide index stream   (narrow == false)
-    DevBuf<int16_t> dcol;          // narrow index stream (narrow == true): col = global row + dcol
+    DevBuf<uint32_t> pcol;         // narrow index stream (narrow == true): two 16-bit offsets from the global row per word
     DevBuf<double> val;
     uint64_t index_bytes() const { return entries * (narrow ? 2ull : 4ull); }
 };
 
 // ---- CSR -> SELL-32 --------------------------------------------------------
 __global__ void sell_width_kernel(const uint32_t *__restrict__ rowptr, uint32_t n_rows,
-                                  uint32_t n_slices, uint32_t *__restrict__ width) {
+                                  uint32_t n_slices, int round_even, uint32_t *__restrict__ width) {
     const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t len = (row < n_rows) ? rowptr[row + 1] - rowptr[row] : 0u;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, off));
     const uint32_t s = row >> 5;
+    if (round_even) len = (len + 1u) & ~1u;      // narrow index stream packs two offsets per word
     if ((threadIdx.x & 31) == 0 && s < n_slices) width[s] = len;
 }
 
@@ -61,12 +62,13 @@ __global__ void band_width_kernel(const uint32_t *__restrict__ rowptr, const int
     if ((threadIdx.x & 31) == 0 && b) atomicMax(band, b);
 }
 
-template <class IDX>
+// Wide: scol[base + k*32 + lane] = absolute column.  Narrow: the slice width is even and
+// pcol[base/2 + (k/2)*32 + lane] packs the 16-bit offsets (column - global row) of entries k and k+1.
+template <bool NARROW>
 __global__ void sell_fill_kernel(const uint32_t *__restrict__ rowptr, const int32_t *__restrict__ ccol,
                                  const double *__restrict__ cval, uint32_t n_rows, uint32_t row_lo,
-                                 const uint32_t *__restrict__ slice_off, IDX *__restrict__ scol,
-                                 double *__restrict__ sval) {
-    constexpr bool kNarrow = sizeof(IDX) == 2;
+                                 const uint32_t *__restrict__ slice_off, int32_t *__restrict__ scol,
+                                 uint32_t *__restrict__ pcol, double *__restrict__ sval) {
     const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t s = row >> 5, lane = threadIdx.x & 31;
     // whole warps stay together: a slice is written by the warp that owns it
@@ -74,15 +76,23 @@ __global__ void sell_fill_kernel(const uint32_t *__restrict__ rowptr, const int3
     if (s >= n_slices) return;
     const uint32_t w = slice_off[s + 1] - slice_off[s];
     const size_t base = (size_t)slice_off[s] * 32 + lane;
+    const size_t pbase = (size_t)slice_off[s] * 16 + lane;
     const uint32_t p0 = (row < n_rows) ? rowptr[row] : 0u;
     const uint32_t len = (row < n_rows) ? rowptr[row + 1] - p0 : 0u;
     // padding multiplies 0.0 by x at the row's own column (x is padded by 32 finite entries)
     const int32_t grow = (int32_t)(row_lo + row);
+    uint32_t pack = 0;
     for (uint32_t k = 0; k < w; ++k) {
         const bool real = k < len;
         const int32_t c = real ? ccol[p0 + k] : grow;
-        scol[base + (size_t)k * 32] = kNarrow ? (IDX)(c - grow) : (IDX)c;
         sval[base + (size_t)k * 32] = real ? cval[p0 + k] : 0.0;
+        if (NARROW) {
+            const uint32_t d = (uint32_t)(uint16_t)(int16_t)(c - grow);
+            if (k & 1u) pcol[pbase + (size_t)(k >> 1) * 32] = pack | (d << 16);
+            else pack = d;
+        } else {
+            scol[base + (size_t)k * 32] = c;
+        }
     }
 }
 
@@ -90,16 +100,11 @@ inline void build_sell(mag_ctx *ctx, const CsrMatrix &A, SellMatrix &S, bool all
     S.n_rows = A.n_rows; S.row_lo = A.row_lo;
     S.n_slices = (A.n_rows + 31) / 32;
     S.slice_off.alloc(ctx, (size_t)S.n_slices + 1);
-    if (S.n_slices == 0) { S.entries = 0; S.slice_off.zero(); S.col.alloc(ctx, 0); S.val.alloc(ctx, 0); return; }
+    if (S.n_slices == 0) {
+        S.entries = 0; S.narrow = false; S.slice_off.zero(); S.col.alloc(ctx, 0); S.val.alloc(ctx, 0);
+        return;
+    }
     const unsigned blocks = cdiv((size_t)S.n_slices * 32, 256);
-    MAG_LAUNCH(ctx, sell_width_kernel, blocks, 256, 0, (const uint32_t *)A.rowptr.p, A.n_rows,
-               S.n_slices, S.slice_off.p);
-    exclusive_scan_u32(ctx, S.slice_off.p, S.n_slices, S.slice_off.p, (size_t)S.n_slices + 1);
-    uint32_t groups = 0;
-    MAG_CUDA(cudaMemcpyAsync(&groups, S.slice_off.p + S.n_slices, sizeof(uint32_t),
-                             cudaMemcpyDeviceToHost, ctx->stream));
-    MAG_CUDA(cudaStreamSynchronize(ctx->stream));
-    S.entries = (uint64_t)groups * 32;
     int h_band = 0;
     {
         DevBuf<int> band(ctx, 1);
@@ -110,17 +115,25 @@ inline void build_sell(mag_ctx *ctx, const CsrMatrix &A, SellMatrix &S, bool all
         MAG_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     S.narrow = allow_narrow && h_band < 32768;
+    MAG_LAUNCH(ctx, sell_width_kernel, blocks, 256, 0, (const uint32_t *)A.rowptr.p, A.n_rows,
+               S.n_slices, S.narrow ? 1 : 0, S.slice_off.p);
+    exclusive_scan_u32(ctx, S.slice_off.p, S.n_slices, S.slice_off.p, (size_t)S.n_slices + 1);
+    uint32_t groups = 0;
+    MAG_CUDA(cudaMemcpyAsync(&groups, S.slice_off.p + S.n_slices, sizeof(uint32_t),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+    S.entries = (uint64_t)groups * 32;
     S.val.alloc(ctx, S.entries);
     if (S.narrow) {
-        S.dcol.alloc(ctx, S.entries);
-        MAG_LAUNCH(ctx, sell_fill_kernel<int16_t>, blocks, 256, 0, (const uint32_t *)A.rowptr.p,
+        S.pcol.alloc(ctx, S.entries / 2);
+        MAG_LAUNCH(ctx, sell_fill_kernel<true>, blocks, 256, 0, (const uint32_t *)A.rowptr.p,
                    (const int32_t *)A.col.p, (const double *)A.val.p, A.n_rows, A.row_lo,
-                   (const uint32_t *)S.slice_off.p, S.dcol.p, S.val.p);
+                   (const uint32_t *)S.slice_off.p, (int32_t *)nullptr, S.pcol.p, S.val.p);
     } else {
         S.col.alloc(ctx, S.entries);
-        MAG_LAUNCH(ctx, sell_fill_kernel<int32_t>, blocks, 256, 0, (const uint32_t *)A.rowptr.p,
+        MAG_LAUNCH(ctx, sell_fill_kernel<false>, blocks, 256, 0, (const uint32_t *)A.rowptr.p,
                    (const int32_t *)A.col.p, (const double *)A.val.p, A.n_rows, A.row_lo,
-                   (const uint32_t *)S.slice_off.p, S.col.p, S.val.p);
+                   (const uint32_t *)S.slice_off.p, S.col.p, (uint32_t *)nullptr, S.val.p);
     }
 }
 
@@ -198,30 +211,48 @@ __device__ __forceinline__ double sell_rows(const uint32_t *__restrict__ slice_o
                                             const double *__restrict__ sval,
                                             const double *__restrict__ x, double *__restrict__ y,
                                             uint32_t n_rows, uint32_t n_slices, uint32_t row_lo) {
-    constexpr bool kNarrow = sizeof(IDX) == 2;
+    constexpr bool kNarrow = sizeof(IDX) == 2;     // IDX = int16_t selects the packed-offset stream
     const int lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     double dot = 0.0;
     for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slices; s += warps) {
         const uint32_t o0 = __ldg(&slice_off[s]), o1 = __ldg(&slice_off[s + 1]);
         const double *v = sval + (size_t)o0 * 32 + lane;
-        const IDX *c = scol + (size_t)o0 * 32 + lane;
         const uint32_t w = o1 - o0;
         const uint32_t row = s * 32 + lane;
-        // narrow: the stream holds offsets from the row's own (global) column
-        const double *xb = kNarrow ? x + (row_lo + row) : x;
         double acc0 = 0.0, acc1 = 0.0;
         uint32_t k = 0;
-        for (; k + 4 <= w; k += 4) {
-            const double a0 = __ldcs(v + (size_t)(k + 0) * 32), a1 = __ldcs(v + (size_t)(k + 1) * 32);
-            const double a2 = __ldcs(v + (size_t)(k + 2) * 32), a3 = __ldcs(v + (size_t)(k + 3) * 32);
-            const int c0 = __ldcs(c + (size_t)(k + 0) * 32), c1 = __ldcs(c + (size_t)(k + 1) * 32);
-            const int c2 = __ldcs(c + (size_t)(k + 2) * 32), c3 = __ldcs(c + (size_t)(k + 3) * 32);
-            const double x0 = __ldg(xb + c0), x1 = __ldg(xb + c1), x2 = __ldg(xb + c2), x3 = __ldg(xb + c3);
-            acc0 = fma(a0, x0, acc0); acc1 = fma(a1, x1, acc1);
-            acc0 = fma(a2, x2, acc0); acc1 = fma(a3, x3, acc1);
+        if (kNarrow) {
+            // two offsets per 32-bit word: every index load of the warp is one full 128-byte line
+            const uint32_t *pc = reinterpret_cast<const uint32_t *>(scol) + (size_t)o0 * 16 + lane;
+            const double *xb = x + (row_lo + row);
+            for (; k + 4 <= w; k += 4) {
+                const double a0 = __ldcs(v + (size_t)(k + 0) * 32), a1 = __ldcs(v + (size_t)(k + 1) * 32);
+                const double a2 = __ldcs(v + (size_t)(k + 2) * 32), a3 = __ldcs(v + (size_t)(k + 3) * 32);
+                const uint32_t p0 = __ldcs(pc + (size_t)(k >> 1) * 32), p1 = __ldcs(pc + (size_t)((k >> 1) + 1) * 32);
+                const double x0 = __ldg(xb + (int)(short)(p0 & 0xffffu)), x1 = __ldg(xb + ((int)p0 >> 16));
+                const double x2 = __ldg(xb + (int)(short)(p1 & 0xffffu)), x3 = __ldg(xb + ((int)p1 >> 16));
+                acc0 = fma(a0, x0, acc0); acc1 = fma(a1, x1, acc1);
+                acc0 = fma(a2, x2, acc0); acc1 = fma(a3, x3, acc1);
+            }
+            for (; k < w; k += 2) {        // w is even in narrow mode
+                const uint32_t p0 = __ldcs(pc + (size_t)(k >> 1) * 32);
+                acc0 = fma(__ldcs(v + (size_t)k * 32), __ldg(xb + (int)(short)(p0 & 0xffffu)), acc0);
+                acc1 = fma(__ldcs(v + (size_t)(k + 1) * 32), __ldg(xb + ((int)p0 >> 16)), acc1);
+            }
+        } else {
+            const IDX *c = scol + (size_t)o0 * 32 + lane;
+            for (; k + 4 <= w; k += 4) {
+                const double a0 = __ldcs(v + (size_t)(k + 0) * 32), a1 = __ldcs(v + (size_t)(k + 1) * 32);
+                const double a2 = __ldcs(v + (size_t)(k + 2) * 32), a3 = __ldcs(v + (size_t)(k + 3) * 32);
+                const int c0 = __ldcs(c + (size_t)(k + 0) * 32), c1 = __ldcs(c + (size_t)(k + 1) * 32);
+                const int c2 = __ldcs(c + (size_t)(k + 2) * 32), c3 = __ldcs(c + (size_t)(k + 3) * 32);
+                const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+                acc0 = fma(a0, x0, acc0); acc1 = fma(a1, x1, acc1);
+                acc0 = fma(a2, x2, acc0); acc1 = fma(a3, x3, acc1);
+            }
+            for (; k < w; ++k) acc0 = fma(__ldcs(v + (size_t)k * 32), __ldg(x + (int)__ldcs(c + (size_t)k * 32)), acc0);
         }
-        for (; k < w; ++k) acc0 = fma(__ldcs(v + (size_t)k * 32), __ldg(xb + (int)__ldcs(c + (size_t)k * 32)), acc0);
         if (row < n_rows) {
             const double yi = acc0 + acc1;
             y[row] = yi;
