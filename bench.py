@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--spmv-reps", type=int, default=100)
     ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
                     help="c4: the 16 M-DOF plate (strong scaling); c5: perforated plate, 16 M DOF per GPU (weak scaling)")
+    ap.add_argument("--spmv-format", type=int, default=0, help="0 SELL-32 (default), 4 SELL-32 with packed 16-bit column offsets")
     ap.add_argument("--allreduce", type=int, default=0, help="multi-GPU dot products: 0 peer-memory mailbox, 1 NCCL")
     return ap.parse_args()
 
@@ -226,7 +227,7 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     meta = meshgen.EXAMPLE_MATERIAL
     mat = _material(meta)
-    opt = _lib.default_options(stream=stream.cuda_stream, allreduce=args.allreduce)
+    opt = _lib.default_options(stream=stream.cuda_stream, allreduce=args.allreduce, spmv_format=args.spmv_format)
     nx, ny = args.nx, args.ny
     weak = args.workload == "c5"
     if weak:                                   # BASELINE configs[4]: 16 M DOF per GPU, perforated
