@@ -391,7 +391,10 @@ def run_ours(args):
                     "pcg_final_rel_residual": last.final_residual / last.b_norm if last.b_norm else 0.0,
                     "spmv_hbm_gbs": achieved, "ms_elem": last.ms_elem, "ms_sort": last.ms_sort,
                     "ms_reduce": last.ms_reduce, "ms_bc": last.ms_bc, "ms_format": last.ms_format,
-                    "ms_post": last.ms_post, "two_level": two_level},
+                    "ms_post": last.ms_post, "two_level": two_level,
+                    # device-side timeline of one PCG iteration on rank 0 (%globaltimer, us): update_p + launch gap,
+                    # spmv, gap, wait for global p.q, update_xr (incl. wait), gap, wait for global r.z
+                    "pcg_iteration_timeline_us": [round(v / 1e3, 2) for v in list(last.prof)[:7]]},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

@@ -109,8 +109,8 @@ inline void build_sell(mag_ctx *ctx, const CsrMatrix &A, SellMatrix &S, bool all
         return;
     }
     const unsigned blocks = cdiv((size_t)S.n_slices * 32, 256);
-    int h_band = 0;
-    {
+    int h_band = 1 << 30;
+    if (allow_narrow) {
         DevBuf<int> band(ctx, 1);
         band.zero();
         MAG_LAUNCH(ctx, band_width_kernel, blocks, 256, 0, (const uint32_t *)A.rowptr.p, (const int32_t *)A.col.p,
