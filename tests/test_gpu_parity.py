@@ -439,3 +439,67 @@ def test_narrow_and_wide_sell_index_streams_agree(ctx):
         xs = np.random.default_rng(6).normal(size=S.n_free)
         rp, col, val, rhs, fmap = S.export_kff()
         assert rel_l2(S.spmv(xs, fmt=2), O.spmv((rp, col, val), xs)) < 1e-14
+
+
+def _random_bc_mesh(seed, nx=26, ny=17):
+    """Jittered plate with a random, per-DOF consistent boundary pattern: random nodes get prescribed
+    displacements (possibly one axis only) and random free DOFs get non-zero applied forces."""
+    rng = np.random.default_rng(seed)
+    m = meshgen.jitter(meshgen.plate(nx, ny), seed=seed).copy()
+    n = m.n_nodes
+    m.known[:] = 4 | 8                                   # everything free, forces known (= 0)
+    m.ux[:] = 0; m.uy[:] = 0; m.fx[:] = 0; m.fy[:] = 0
+    fixed = rng.choice(n, size=max(4, n // 12), replace=False)
+    for i in fixed:
+        kind = rng.integers(0, 3)
+        if kind in (0, 2):
+            m.known[i] = (int(m.known[i]) & 0xfb) | 1; m.ux[i] = rng.normal() * 1e-3
+        if kind in (1, 2):
+            m.known[i] = (int(m.known[i]) & 0xf7) | 2; m.uy[i] = rng.normal() * 1e-3
+    loaded = rng.choice(np.setdiff1d(np.arange(n), fixed), size=n // 10, replace=False)
+    m.fx[loaded] = rng.normal(size=loaded.size) * 1e6
+    m.fy[loaded] = rng.normal(size=loaded.size) * 1e6
+    m.known[0] = 3; m.ux[0] = m.uy[0] = 0.0; m.known[1] = 3   # no rigid-body mode left
+    m.fx[[0, 1]] = 0; m.fy[[0, 1]] = 0
+    return m
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_boundary_patterns_and_force_loads(ctx, seed):
+    mesh = _random_bc_mesh(seed)
+    om = O.Mesh(mesh)
+    full_ref = O.assemble_sparse(om, O.element_stiffness(om, META))
+    (rp_r, col_r, val_r), rhs_r, fmap_r = O.partition(om, full_ref, dense=False)
+    with solver.System(mesh, META, ctx) as S:
+        rp, col, val, rhs, fmap = S.export_kff()
+        assert np.array_equal(rp, rp_r) and np.array_equal(col, col_r) and np.array_equal(fmap, fmap_r)
+        assert np.array_equal(val, val_r) and np.array_equal(rhs, rhs_r)          # applied forces enter the rhs
+        sol = S.solve(compat())
+    ref = O.run(om, META, O.cg_options(), dense=True)
+    assert rel_l2(np.concatenate([sol.ux, sol.uy]), np.concatenate([ref["ux"], ref["uy"]])) < 1e-9
+    assert np.abs(sol.stress - ref["stress"]).max() / np.abs(ref["stress"]).max() < 1e-8
+    f, fr = np.concatenate([sol.fx, sol.fy]), np.concatenate([ref["fx"], ref["fy"]])
+    assert np.abs(f - fr).max() / np.abs(fr).max() < 1e-8
+    vr = solver.virtual_rank_solve(mesh, META, 3, ctx, compat())
+    assert rel_l2(np.concatenate([vr.ux, vr.uy]), np.concatenate([ref["ux"], ref["uy"]])) < 1e-9
+
+
+def test_rows_by_force_columns_by_displacement(ctx):
+    """The reference picks ROWS by `force known` and COLUMNS by `displacement unknown`
+    (solver.rs:380-396) and only needs the two COUNTS to agree.  A DOF with both known plus a DOF with
+    neither keeps the counts equal while the two sets differ: the elimination must still reproduce the
+    oracle's (non-symmetric) K_ff, rhs and numbering bit for bit."""
+    mesh = meshgen.jitter(meshgen.plate(9, 6)).copy()
+    a, b = 25, 46                                       # interior nodes with fx = fy = Some(0)
+    mesh.known[a] = 1 | 4 | 8; mesh.ux[a] = 2e-3        # x: displacement AND force known
+    mesh.known[b] = 8                                   # x: neither known
+    om = O.Mesh(mesh)
+    full_ref = O.assemble_sparse(om, O.element_stiffness(om, META))
+    (rp_r, col_r, val_r), rhs_r, fmap_r = O.partition(om, full_ref, dense=False)
+    with solver.System(mesh, META, ctx) as S:
+        rp, col, val, rhs, fmap = S.export_kff()
+    assert np.array_equal(rp, rp_r) and np.array_equal(col, col_r) and np.array_equal(val, val_r)
+    assert np.array_equal(rhs, rhs_r) and np.array_equal(fmap, fmap_r)
+    import scipy.sparse as sp
+    A = sp.csr_matrix((val, col, rp), shape=(len(rhs), len(rhs)))
+    assert abs(A - A.T).max() > 0                        # really the unsymmetric case
