@@ -164,6 +164,10 @@ int mag_element_stiffness(mag_ctx *ctx, const mag_mesh *mesh, const mag_material
                           double *ke /* n_elems*36 */);
 /* signed areas (solver.rs:187-193, pub: used by mesher::check_ccw). */
 int mag_element_area(mag_ctx *ctx, const mag_mesh *mesh, double *area /* n_elems */);
+/* B of every element, 3x6 row-major: solver::compute_strain_displacement_matrix (solver.rs:204-230, pub). */
+int mag_strain_displacement(mag_ctx *ctx, const mag_mesh *mesh, double *b /* n_elems*18 */);
+/* D, 3x3 row-major: solver::compute_stress_strain_matrix (solver.rs:240-250, pub). Host only. */
+int mag_stress_strain(double poisson_ratio, double youngs_modulus, double *d /* 9 */);
 /* stress recovery only (solver.rs:496-535). */
 int mag_stress(mag_ctx *ctx, const mag_mesh *mesh, const mag_material *mat, const double *ux,
                const double *uy, double *stress, double *sigma /*or NULL*/);

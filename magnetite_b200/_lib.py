@@ -93,6 +93,8 @@ _SIGNATURES = {
     "mag_system_export_full": (C.c_int, [_vp, _vp, _vp, _vp]),
     "mag_element_stiffness": (C.c_int, [_vp, C.POINTER(MagMesh), C.POINTER(MagMaterial), _vp]),
     "mag_element_area": (C.c_int, [_vp, C.POINTER(MagMesh), _vp]),
+    "mag_strain_displacement": (C.c_int, [_vp, C.POINTER(MagMesh), _vp]),
+    "mag_stress_strain": (C.c_int, [C.c_double, C.c_double, _vp]),
     "mag_stress": (C.c_int, [_vp, C.POINTER(MagMesh), C.POINTER(MagMaterial), _vp, _vp, _vp, _vp]),
     "mag_system_spmv": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "mag_system_spmv_bench": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),

@@ -294,6 +294,35 @@ extern "C" int mag_element_area(mag_ctx *ctx, const mag_mesh *m, double *area) {
     });
 }
 
+// B (3x6 row-major) of every element: solver::compute_strain_displacement_matrix (solver.rs:204-230).
+extern "C" int mag_strain_displacement(mag_ctx *ctx, const mag_mesh *m, double *b_out) {
+    return guarded([&] {
+        CallScope scope(ctx, nullptr);
+        check_mesh_args(m);
+        if (m->n_elems && !b_out) fail(MAG_ERR_BAD_ARG, "null argument");
+        DevBuf<double2> xy; DevBuf<uint32_t> n0, n1, n2;
+        upload_geometry(ctx, m, xy, n0, n1, n2);
+        const size_t E = m->n_elems;
+        DevBuf<double> out(ctx, E * 18);
+        if (E)
+            MAG_LAUNCH(ctx, strain_displacement_kernel, cdiv(E, 256), 256, 0, (const double2 *)xy.p,
+                       (const uint32_t *)n0.p, (const uint32_t *)n1.p, (const uint32_t *)n2.p, E, out.p);
+        copy_from_device(ctx, b_out, (const double *)out.p, E * 18, false);
+        MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+// D (3x3 row-major): solver::compute_stress_strain_matrix (solver.rs:240-250) — the constant the
+// kernels keep in __constant__ memory.  Host arithmetic, no device needed.
+extern "C" int mag_stress_strain(double poisson_ratio, double youngs_modulus, double *d_out) {
+    return guarded([&] {
+        if (!d_out) fail(MAG_ERR_BAD_ARG, "null argument");
+        const mag_material m{youngs_modulus, poisson_ratio, 1.0};
+        const MaterialConst c = make_material(m);
+        for (int i = 0; i < 9; ++i) d_out[i] = c.D[i];
+    });
+}
+
 extern "C" int mag_stress(mag_ctx *ctx, const mag_mesh *m, const mag_material *mat, const double *ux,
                           const double *uy, double *stress, double *sigma) {
     return guarded([&] {

@@ -158,6 +158,21 @@ element_stiffness_kernel(const double2 *__restrict__ xy, const uint32_t *__restr
     }
 }
 
+// B of every element, row-major 3x6 (solver.rs:204-230) — parity export of the pub function.
+__global__ void strain_displacement_kernel(const double2 *__restrict__ xy, const uint32_t *__restrict__ n0,
+                                           const uint32_t *__restrict__ n1, const uint32_t *__restrict__ n2,
+                                           size_t n_elems, double *__restrict__ out) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_elems) return;
+    const Tri t = load_tri(xy, n0[e], n1[e], n2[e]);
+    double B[3][6];
+    tri_B(t, tri_area(t), B);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) out[e * 18 + r * 6 + c] = B[r][c];
+}
+
 // solver.rs:496-535.  sigma = (D*B)*u_e; sign = -1 iff sx+sy < 1.0;
 // stress = sqrt(sx^2 + sy^2) * sign.  sigma3 (optional) receives sx,sy,txy.
 __global__ void __launch_bounds__(256)

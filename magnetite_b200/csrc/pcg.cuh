@@ -56,6 +56,8 @@ struct PcgScalars {
     unsigned long long iter, max_iter;
     unsigned long long chunk_base;   // iterations completed when the current graph launch started
     unsigned long long epoch;   // solve counter: makes sequence numbers unique across solves
+    double best_rr;             // lowest r.r seen so far and the iteration that produced it (argmin's
+    unsigned long long best_iter;   // best_param: IterState::update keeps the iterate with the lowest cost)
     int stop;            // 1: converged, 2: max_iter, 3: breakdown, 4: peer timeout
     unsigned ticket_a, ticket_b;
     int tune;            // debug switches (MAG_TUNE): 1 = no halo stores, 2 = no timeline, 4 = poll backoff
@@ -326,6 +328,7 @@ pcg_update_p_kernel(double *__restrict__ p, const double *__restrict__ r,
         const unsigned long long it = sc->iter + 1;
         if (sc->iter == 0) sc->first_pq = pq;
         sc->iter = it;
+        if (rr < sc->best_rr) { sc->best_rr = rr; sc->best_iter = it; }
         if (sc->stop == 4) {}                                   // a peer never answered
         else if (!(pq != 0.0) || !(rr == rr)) sc->stop = 3;     // breakdown / NaN
         else if (rr <= sc->thr2) sc->stop = 1;

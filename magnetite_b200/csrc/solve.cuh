@@ -340,6 +340,7 @@ struct SolveOutcome {
     double bb = 0.0;
     float ms_coarse_setup = 0.f;
     uint32_t n_coarse = 0;
+    bool rerun_best = false;
 };
 
 // Runs CG over `ranks` (size 1 in production).  All ranks see identical scalars.
@@ -399,12 +400,14 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
         std::memset(&init, 0, sizeof init);
         init.pair[0][0] = hs.pair[0][0]; init.pair[0][1] = hs.pair[0][1];
         init.thr2 = thr2; init.max_iter = opt.max_iter; init.stop = stop0;
+        init.best_rr = bb; init.best_iter = 0;
         init.epoch = W.S->solve_epoch;
         init.tune = ctx->tune;
         MAG_CUDA(cudaMemcpyAsync(W.scal.p, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
     }
     MAG_CUDA(cudaStreamSynchronize(ctx->stream));
     hs.thr2 = thr2; hs.stop = stop0; hs.iter = 0;
+    hs.best_rr = bb; hs.best_iter = 0;
     if (stop0) return out;
 
     cudaGraph_t graph = nullptr;
@@ -458,12 +461,28 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
     return out;
 }
 
+// compat mode = the reference's Executor: it returns `best_param`, the iterate with the lowest cost
+// (solver.rs:167-176).  When the target cost is reached that is the last iterate.  When max_iters ends
+// the run it may be an earlier one: CG is deterministic here, so the solve is simply repeated up to that
+// iteration instead of copying x aside on every improvement.
+static SolveOutcome pcg_drive_best(mag_ctx *ctx, std::vector<RankState> &ranks, const mag_options &opt) {
+    SolveOutcome o = pcg_drive(ctx, ranks, opt);
+    if (opt.compat && o.hs.stop == 2 && o.hs.best_iter != o.hs.iter) {
+        mag_options again = opt;
+        again.max_iter = o.hs.best_iter;
+        const SolveOutcome b = pcg_drive(ctx, ranks, again);
+        o.hs.best_rr = b.hs.iter ? b.hs.pair[b.hs.iter & 1][1] : b.bb;
+        o.rerun_best = true;
+    }
+    return o;
+}
+
 static void fill_solve_stats(mag_stats &st, const SolveOutcome &o, uint32_t n_glob) {
     const PcgScalars &hs = o.hs;
     const int last = (int)(hs.iter & 1);      // pair[] slot written by the last completed iteration
     st.iters = hs.iter;
     st.b_norm = std::sqrt(o.bb);
-    st.final_residual = std::sqrt(hs.iter ? hs.pair[last][1] : o.bb);
+    st.final_residual = std::sqrt(o.rerun_best ? hs.best_rr : (hs.iter ? hs.pair[last][1] : o.bb));
     st.converged = (hs.stop == 1) || n_glob == 0;
     st.ms_coarse_setup = o.ms_coarse_setup;
     st.n_coarse = o.n_coarse;
@@ -515,14 +534,14 @@ static void download_result(mag_ctx *ctx, const mag_system *S, PostBuffers &B, m
     if (want_sigma) copy_from_device(ctx, out->sigma, (const double *)B.sigma.p, E * 3, odev);
 }
 
-static void raise_solver_status(const SolveOutcome &o, const mag_stats &st) {
+static void raise_solver_status(const SolveOutcome &o, const mag_stats &st, bool compat = false) {
     if (o.hs.stop == 4)
         fail(MAG_ERR_NCCL, "a peer GPU never delivered its share of a dot product (iteration %llu): "
                            "a rank has crashed or the ranks are out of step", (unsigned long long)o.hs.iter);
     if (o.hs.stop == 3)
         fail(MAG_ERR_INDEFINITE, "conjugate gradient broke down at iteration %llu (p.Ap = %g, r.r = %g)",
              (unsigned long long)o.hs.iter, o.hs.pq, st.final_residual * st.final_residual);
-    if (o.hs.stop == 2)
+    if (o.hs.stop == 2 && !compat)      // the reference returns Ok(best_param) when max_iters ends the run
         fail(MAG_ERR_NOT_CONVERGED, "conjugate gradient stopped at max_iter = %llu with ||r|| = %g",
              (unsigned long long)o.hs.iter, st.final_residual);
 }
@@ -542,7 +561,7 @@ static void solve_impl(mag_system *S, const mag_options *opt_in, mag_result *out
     if (S->nranks > 1) setup_halo_ipc(ctx, S);
     std::vector<RankState> ranks(1);
     rank_alloc(ctx, ranks[0], S);
-    SolveOutcome o = pcg_drive(ctx, ranks, opt);
+    SolveOutcome o = pcg_drive_best(ctx, ranks, opt);
     fill_solve_stats(st, o, S->n_free);
     st.ms_solve = phase.stop();
 
@@ -570,7 +589,7 @@ static void solve_impl(mag_system *S, const mag_options *opt_in, mag_result *out
     st.kernel_launches = ctx->launches - launches_before;
     S->stats.iters = st.iters;
     if (stats_out) *stats_out = st;
-    raise_solver_status(o, st);
+    raise_solver_status(o, st, opt.compat != 0);
 }
 
 // Single-process emulation of an R-rank solve on one GPU (tests): the mesh is assembled R
@@ -600,7 +619,7 @@ static void virtual_solve_impl(mag_ctx *ctx, const mag_mesh *mesh, const mag_mat
     for (int r = 0; r < R; ++r) rank_alloc(ctx, ranks[r], sys[r].get());
     EventTimer phase(ctx->stream);
     phase.start();
-    SolveOutcome o = pcg_drive(ctx, ranks, opt);
+    SolveOutcome o = pcg_drive_best(ctx, ranks, opt);
     mag_stats st = sys[0]->stats;
     fill_solve_stats(st, o, sys[0]->n_free);
     st.ms_solve = phase.stop();
@@ -623,7 +642,7 @@ static void virtual_solve_impl(mag_ctx *ctx, const mag_mesh *mesh, const mag_mat
     MAG_CUDA(cudaStreamSynchronize(ctx->stream));
     st.kernel_launches = launches + ctx->launches;
     if (stats_out) *stats_out = st;
-    raise_solver_status(o, st);
+    raise_solver_status(o, st, opt.compat != 0);
 }
 
 }  // namespace mag

@@ -231,9 +231,33 @@ def stress_soa(mesh: MeshSoA, meta: ModelMetadata, ux, uy, want_sigma=False, ctx
     return (s, sig) if want_sigma else s
 
 
+def strain_displacement_matrices(mesh: MeshSoA, ctx: Optional[_lib.Context] = None) -> np.ndarray:
+    """B of every element, (E, 3, 6) (solver.rs:204-230), in one launch."""
+    ctx = ctx or default_context()
+    m = mesh.normalised()
+    ms = _mesh_struct(m)
+    b = np.empty((m.n_elems, 3, 6), np.float64)
+    check(load().mag_strain_displacement(ctx.handle, C.byref(ms), ptr(b)), "mag_strain_displacement")
+    return b
+
+
 # ---------------------------------------------------------------------------
 # the reference's public functions
 # ---------------------------------------------------------------------------
+def compute_stress_strain_matrix(poisson_ratio: float, youngs_modulus: float) -> np.ndarray:
+    """solver::compute_stress_strain_matrix (solver.rs:240-250): plane-stress D, 3x3."""
+    d = np.empty(9, np.float64)
+    check(load().mag_stress_strain(float(poisson_ratio), float(youngs_modulus), ptr(d)), "mag_stress_strain")
+    return d.reshape(3, 3)
+
+
+def compute_strain_displacement_matrix(element: Element, nodes: Sequence[Node], element_area: float = None) -> np.ndarray:
+    """solver::compute_strain_displacement_matrix (solver.rs:204-230): B of one element, 3x6.  The
+    reference takes the (signed) area as an argument; here it is recomputed on the device."""
+    tri = [nodes[i] for i in element.nodes]
+    return strain_displacement_matrices(MeshSoA.from_aos(tri, [Element([0, 1, 2])]))[0]
+
+
 def compute_element_area(element: Element, nodes: Sequence[Node]) -> float:
     """solver::compute_element_area (solver.rs:187-193) — signed area of one element.
     (mesher.check_ccw uses the batched `element_areas` instead of calling this per element.)"""

@@ -165,3 +165,11 @@ def test_cpp_host_layer_formats_like_rust(built):
     subprocess.run(["make", "-C", str(ROOT / "host")], check=True, capture_output=True)
     r = subprocess.run([str(exe), "--format-selftest"], capture_output=True, text=True)
     assert r.returncode == 0 and "FORMAT_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_stress_strain_matrix_matches_oracle(built):
+    """solver::compute_stress_strain_matrix is host arithmetic in the library: bit-identical to the oracle."""
+    from magnetite_b200 import solver
+    from oracle import oracle as O
+    for nu, E in ((0.33, 69e9), (0.25, 210e9), (0.0, 1.0), (0.49, 3e6)):
+        assert np.array_equal(solver.compute_stress_strain_matrix(nu, E), O.stress_strain(nu, E))

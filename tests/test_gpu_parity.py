@@ -503,3 +503,31 @@ def test_rows_by_force_columns_by_displacement(ctx):
     import scipy.sparse as sp
     A = sp.csr_matrix((val, col, rp), shape=(len(rhs), len(rhs)))
     assert abs(A - A.T).max() > 0                        # really the unsymmetric case
+
+
+def test_public_element_functions(ctx):
+    """The pub functions of solver.rs besides run(): area, B and D, against the numpy twin."""
+    from oracle import reference_semantics as R
+    mesh = meshgen.jitter(meshgen.plate(6, 4))
+    Bs = solver.strain_displacement_matrices(mesh, ctx)
+    conn = np.stack([mesh.n0, mesh.n1, mesh.n2], 1).astype(int)
+    for e in (0, 7, len(conn) - 1):
+        assert np.array_equal(Bs[e], R.B_matrix(mesh.x, mesh.y, conn[e], R.area(mesh.x, mesh.y, conn[e])))
+    nodes, elements = mesh.to_aos()
+    assert np.array_equal(solver.compute_strain_displacement_matrix(elements[3], nodes), Bs[3])
+    assert np.array_equal(solver.compute_stress_strain_matrix(0.33, 69e9), R.D_matrix(0.33, 69e9))
+
+
+@pytest.mark.parametrize("max_iter", [0, 1, 20, 21, 33, 58])
+def test_compat_returns_best_param_when_max_iters_ends_the_run(ctx, max_iter):
+    """argmin's Executor hands back best_param (solver.rs:167-176): when max_iters ends the run that is
+    the iterate with the lowest residual norm so far, not necessarily the last one (CG's 2-norm is not
+    monotone: at 21, 33 and 58 iterations on this mesh the last iterate is worse than an earlier one).
+    Like the reference, compat mode does not treat that as an error."""
+    mesh = meshgen.jitter(meshgen.plate(30, 15))
+    ref = O.run(O.Mesh(mesh), META, O.cg_options(max_iter=max_iter), dense=False)
+    sol = solver.solve_soa(mesh, META, ctx, _lib.default_options(compat=1, max_iter=max_iter))
+    assert sol.stats["iters"] == max_iter and sol.stats["converged"] == 0
+    ur = np.concatenate([ref["ux"], ref["uy"]])
+    assert rel_l2(np.concatenate([sol.ux, sol.uy]), ur) < 1e-9
+    assert abs(sol.stats["final_residual"] - ref["stats"]["final_cost"]) <= 1e-9 * ref["stats"]["final_cost"]
