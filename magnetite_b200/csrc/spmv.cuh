@@ -14,6 +14,8 @@
 // The SpMV that runs inside CG also produces the partial dot product p.q, so q
 // is not re-read for it.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -207,8 +209,36 @@ __device__ __forceinline__ bool grid_sum_256(double (&v)[NV], double *__restrict
 }
 
 // ---- SELL-32 SpMV ----------------------------------------------------------
-// One warp per slice, grid-stride over slices.  x is indexed by global column;
-// y by local row.  If DOT, also accumulates sum_i x[row_lo+i]*y[i].
+// Index batch of 4 entries of one lane: four absolute columns (wide) or two words holding four
+// 16-bit offsets from the row's own column (narrow).
+template <class IDX> struct IdxBatch;
+template <> struct IdxBatch<int32_t> {
+    int c0, c1, c2, c3;
+    __device__ __forceinline__ void load(const int32_t *c, uint32_t k) {
+        c0 = __ldcs(c + (size_t)(k + 0) * 32); c1 = __ldcs(c + (size_t)(k + 1) * 32);
+        c2 = __ldcs(c + (size_t)(k + 2) * 32); c3 = __ldcs(c + (size_t)(k + 3) * 32);
+    }
+    __device__ __forceinline__ int o0() const { return c0; }
+    __device__ __forceinline__ int o1() const { return c1; }
+    __device__ __forceinline__ int o2() const { return c2; }
+    __device__ __forceinline__ int o3() const { return c3; }
+};
+template <> struct IdxBatch<int16_t> {
+    uint32_t p0, p1;
+    __device__ __forceinline__ void load(const uint32_t *pc, uint32_t k) {
+        p0 = __ldcs(pc + (size_t)(k >> 1) * 32); p1 = __ldcs(pc + (size_t)((k >> 1) + 1) * 32);
+    }
+    __device__ __forceinline__ int o0() const { return (int)(short)(p0 & 0xffffu); }
+    __device__ __forceinline__ int o1() const { return (int)p0 >> 16; }
+    __device__ __forceinline__ int o2() const { return (int)(short)(p1 & 0xffffu); }
+    __device__ __forceinline__ int o3() const { return (int)p1 >> 16; }
+};
+
+// One warp per slice, grid-stride over slices.  x is indexed by global column; y by local row.
+// If DOT, also accumulates sum_i x[row_lo+i]*y[i].
+// The kernel is latency-bound before it is bandwidth-bound (ncu: long-scoreboard stalls dominate), and
+// the x gathers depend on the index loads, so the index batch of the NEXT four entries is loaded while
+// the current batch's values and gathers are in flight: one memory round trip per batch instead of two.
 template <bool DOT, class IDX>
 __device__ __forceinline__ double sell_rows(const uint32_t *__restrict__ slice_off,
                                             const IDX *__restrict__ scol,
@@ -216,46 +246,40 @@ __device__ __forceinline__ double sell_rows(const uint32_t *__restrict__ slice_o
                                             const double *__restrict__ x, double *__restrict__ y,
                                             uint32_t n_rows, uint32_t n_slices, uint32_t row_lo) {
     constexpr bool kNarrow = sizeof(IDX) == 2;     // IDX = int16_t selects the packed-offset stream
+    using Word = typename std::conditional<kNarrow, uint32_t, int32_t>::type;
     const int lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     double dot = 0.0;
     for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slices; s += warps) {
         const uint32_t o0 = __ldg(&slice_off[s]), o1 = __ldg(&slice_off[s + 1]);
         const double *v = sval + (size_t)o0 * 32 + lane;
+        const Word *c = reinterpret_cast<const Word *>(scol) + (size_t)o0 * (kNarrow ? 16 : 32) + lane;
         const uint32_t w = o1 - o0;
         const uint32_t row = s * 32 + lane;
+        const double *xb = kNarrow ? x + (row_lo + row) : x;    // narrow offsets are relative to the row
         double acc0 = 0.0, acc1 = 0.0;
         uint32_t k = 0;
+        IdxBatch<IDX> cur, nxt;
+        if (w >= 4) nxt.load(c, 0);
+        for (; k + 4 <= w; k += 4) {
+            cur = nxt;
+            if (k + 8 <= w) nxt.load(c, k + 4);                 // next batch's indices, in flight early
+            const double a0 = __ldcs(v + (size_t)(k + 0) * 32), a1 = __ldcs(v + (size_t)(k + 1) * 32);
+            const double a2 = __ldcs(v + (size_t)(k + 2) * 32), a3 = __ldcs(v + (size_t)(k + 3) * 32);
+            const double x0 = __ldg(xb + cur.o0()), x1 = __ldg(xb + cur.o1());
+            const double x2 = __ldg(xb + cur.o2()), x3 = __ldg(xb + cur.o3());
+            acc0 = fma(a0, x0, acc0); acc1 = fma(a1, x1, acc1);
+            acc0 = fma(a2, x2, acc0); acc1 = fma(a3, x3, acc1);
+        }
         if (kNarrow) {
-            // two offsets per 32-bit word: every index load of the warp is one full 128-byte line
-            const uint32_t *pc = reinterpret_cast<const uint32_t *>(scol) + (size_t)o0 * 16 + lane;
-            const double *xb = x + (row_lo + row);
-            for (; k + 4 <= w; k += 4) {
-                const double a0 = __ldcs(v + (size_t)(k + 0) * 32), a1 = __ldcs(v + (size_t)(k + 1) * 32);
-                const double a2 = __ldcs(v + (size_t)(k + 2) * 32), a3 = __ldcs(v + (size_t)(k + 3) * 32);
-                const uint32_t p0 = __ldcs(pc + (size_t)(k >> 1) * 32), p1 = __ldcs(pc + (size_t)((k >> 1) + 1) * 32);
-                const double x0 = __ldg(xb + (int)(short)(p0 & 0xffffu)), x1 = __ldg(xb + ((int)p0 >> 16));
-                const double x2 = __ldg(xb + (int)(short)(p1 & 0xffffu)), x3 = __ldg(xb + ((int)p1 >> 16));
-                acc0 = fma(a0, x0, acc0); acc1 = fma(a1, x1, acc1);
-                acc0 = fma(a2, x2, acc0); acc1 = fma(a3, x3, acc1);
-            }
             for (; k < w; k += 2) {        // w is even in narrow mode
-                const uint32_t p0 = __ldcs(pc + (size_t)(k >> 1) * 32);
+                const uint32_t p0 = __ldcs(reinterpret_cast<const uint32_t *>(c) + (size_t)(k >> 1) * 32);
                 acc0 = fma(__ldcs(v + (size_t)k * 32), __ldg(xb + (int)(short)(p0 & 0xffffu)), acc0);
                 acc1 = fma(__ldcs(v + (size_t)(k + 1) * 32), __ldg(xb + ((int)p0 >> 16)), acc1);
             }
         } else {
-            const IDX *c = scol + (size_t)o0 * 32 + lane;
-            for (; k + 4 <= w; k += 4) {
-                const double a0 = __ldcs(v + (size_t)(k + 0) * 32), a1 = __ldcs(v + (size_t)(k + 1) * 32);
-                const double a2 = __ldcs(v + (size_t)(k + 2) * 32), a3 = __ldcs(v + (size_t)(k + 3) * 32);
-                const int c0 = __ldcs(c + (size_t)(k + 0) * 32), c1 = __ldcs(c + (size_t)(k + 1) * 32);
-                const int c2 = __ldcs(c + (size_t)(k + 2) * 32), c3 = __ldcs(c + (size_t)(k + 3) * 32);
-                const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
-                acc0 = fma(a0, x0, acc0); acc1 = fma(a1, x1, acc1);
-                acc0 = fma(a2, x2, acc0); acc1 = fma(a3, x3, acc1);
-            }
-            for (; k < w; ++k) acc0 = fma(__ldcs(v + (size_t)k * 32), __ldg(x + (int)__ldcs(c + (size_t)k * 32)), acc0);
+            for (; k < w; ++k)
+                acc0 = fma(__ldcs(v + (size_t)k * 32), __ldg(xb + (int)__ldcs(reinterpret_cast<const int32_t *>(c) + (size_t)k * 32)), acc0);
         }
         if (row < n_rows) {
             const double yi = acc0 + acc1;
