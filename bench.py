@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--spmv-reps", type=int, default=100)
     ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
                     help="c4: the 16 M-DOF plate (strong scaling); c5: perforated plate, 16 M DOF per GPU (weak scaling)")
-    ap.add_argument("--spmv-format", type=int, default=0, help="0 SELL-32 (default), 4 SELL-32 with packed 16-bit column offsets")
+    ap.add_argument("--spmv-format", type=int, default=0, help="0 SELL-32 with packed 16-bit column offsets when the band allows (default), 3 SELL-32 with 32-bit columns")
     ap.add_argument("--allreduce", type=int, default=0, help="multi-GPU dot products: 0 peer-memory mailbox, 1 NCCL")
     return ap.parse_args()
 

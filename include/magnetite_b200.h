@@ -85,7 +85,7 @@ typedef struct {
     int32_t cost_kind;       /* compat cost: 0 = ||r||_2 (default), 1 = r.r            */
     int32_t drop_exact_zeros;/* 1 (default): K_ff keeps k != 0.0 only (solver.rs:132)  */
     int32_t check_every;     /* iterations per CUDA-graph chunk between residual polls */
-    int32_t spmv_format;     /* 0/2 SELL-32 (default), 1 scalar CSR, 4 SELL-32 with packed 16-bit column offsets (band < 32768) */
+    int32_t spmv_format;     /* 0/2 SELL-32, packed 16-bit column offsets when the band is < 32768 (default); 1 scalar CSR; 3 SELL-32 with 32-bit columns */
     int32_t want_sigma;      /* also return sx,sy,txy per element                      */
     int32_t allreduce;       /* multi-GPU dot products: 0 peer-memory mailbox (default), 1 NCCL  */
     int32_t coarse_aggregates; /* precond 2: number of aggregates (0 = auto, at most 2048)       */

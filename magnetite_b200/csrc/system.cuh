@@ -307,7 +307,7 @@ static void assemble_impl(mag_ctx *ctx, const mag_mesh *m, const mag_material *m
 
     // ---- solver format -------------------------------------------------------------
     phase.start();
-    build_sell(ctx, A, S->sell, opt && opt->spmv_format == 4);
+    build_sell(ctx, A, S->sell, !(opt && opt->spmv_format == 3));
     st.sell_entries = S->sell.entries;
     st.sell_index_bits = S->sell.narrow ? 16 : 32;
     st.ms_format = phase.stop();

@@ -18,7 +18,7 @@ view = _lib.MagMesh()
 _lib.check(lib.mag_devmesh_view(dm, C.byref(view)), "view")
 m = meshgen.EXAMPLE_MATERIAL
 mat = _lib.MagMaterial(m.youngs_modulus, m.poisson_ratio, m.part_thickness)
-for label, build_fmt, run_fmt in (("SELL-32, 32-bit columns (default)", 0, 2), ("SELL-32, packed 16-bit offsets", 4, 2),
+for label, build_fmt, run_fmt in (("SELL-32, 32-bit columns", 3, 2), ("SELL-32, packed 16-bit offsets (default)", 0, 2),
                                   ("scalar CSR, thread per row", 0, 1)):
     sysh = C.c_void_p(); st = _lib.MagStats()
     _lib.check(lib.mag_assemble(ctx.handle, C.byref(view), C.byref(mat), C.byref(_lib.default_options(spmv_format=build_fmt)),

@@ -426,15 +426,15 @@ def test_narrow_and_wide_sell_index_streams_agree(ctx):
     identical SpMV results and identical CG iterates; unstructured numbering falls back to 32 bits."""
     mesh = meshgen.jitter(meshgen.plate(150, 40))
     x = np.random.default_rng(5).normal(size=2 * mesh.n_nodes)
-    with solver.System(mesh, META, ctx, options=_lib.default_options(spmv_format=4)) as N, solver.System(mesh, META, ctx) as W:
+    with solver.System(mesh, META, ctx) as N, solver.System(mesh, META, ctx, options=_lib.default_options(spmv_format=3)) as W:
         assert N.assemble_stats["sell_index_bits"] == 16 and W.assemble_stats["sell_index_bits"] == 32
         xs = x[: N.n_free]
         assert rel_l2(N.spmv(xs, fmt=2), W.spmv(xs, fmt=2)) < 1e-15      # same products, remainder summed in another order
-        a, b = N.solve(_lib.default_options(spmv_format=4)), W.solve(_lib.default_options())
+        a, b = N.solve(_lib.default_options()), W.solve(_lib.default_options(spmv_format=3))
         assert rel_l2(np.concatenate([a.ux, a.uy]), np.concatenate([b.ux, b.uy])) < 1e-7
         assert abs(int(a.stats["iters"]) - int(b.stats["iters"])) <= 3
     long_plate = meshgen.plate(16500, 1)                           # band 2*(nx+1)+2 > 32767: falls back
-    with solver.System(long_plate, META, ctx, options=_lib.default_options(spmv_format=4)) as S:
+    with solver.System(long_plate, META, ctx) as S:
         assert S.assemble_stats["sell_index_bits"] == 32
         xs = np.random.default_rng(6).normal(size=S.n_free)
         rp, col, val, rhs, fmap = S.export_kff()
