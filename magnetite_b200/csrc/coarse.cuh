@@ -41,6 +41,7 @@ struct CoarseSpace {
     DevBuf<uint32_t> perm;        // local rows sorted by aggregate
     DevBuf<uint32_t> agg_ptr;     // n_agg+1 segment starts into perm
     DevBuf<double> Ainv;          // nc x nc
+    DevBuf<double> Ac_compact;    // n_agg x 81 (setup only)
     DevBuf<double> w, y;          // nc
     DevBuf<double> partials;      // gemv dot partials
     DevBuf<unsigned> ticket;
@@ -152,8 +153,24 @@ coarse_galerkin_kernel(const uint32_t *__restrict__ agg_ptr, const uint32_t *__r
             acc = fma(pia * val[e], pjb, acc);
         }
     }
-    if (live) Ac[(size_t)(3u * I + alpha) * nc + 3u * J + beta] = acc;
+    // compact block row: Ac[I][k][alpha][beta], 81 doubles per aggregate (summed over ranks before it
+    // is expanded to the dense matrix: 1.3 MB on the wire instead of nc^2 * 8 = 302 MB)
+    if (t < 81) Ac[(size_t)I * 81 + t] = live ? acc : 0.0;
     if (t == 0 && far_local) *far = 1;
+    (void)nc;
+}
+
+// dense[3I+alpha][3J+beta] = compact[I][k][alpha][beta] for the (up to) nine neighbours J of I
+__global__ void coarse_expand_kernel(const double *__restrict__ compact, uint32_t nbx, uint32_t nby, uint32_t nc,
+                                     double *__restrict__ dense) {
+    const uint32_t I = blockIdx.x;
+    const int t = threadIdx.x;
+    if (t >= 81) return;
+    const int k = t / 9, alpha = (t % 9) / 3, beta = t % 3;
+    const int jx = (int)(I % nbx) + (k % 3) - 1, jy = (int)(I / nbx) + (k / 3) - 1;
+    if (jx < 0 || jy < 0 || jx >= (int)nbx || jy >= (int)nby) return;
+    const uint32_t J = (uint32_t)(jy * (int)nbx + jx);
+    dense[(size_t)(3u * I + alpha) * nc + 3u * J + beta] = compact[(size_t)I * 81 + t];
 }
 
 // empty aggregates (holes, boxes outside the part) and modes without support: unit diagonal

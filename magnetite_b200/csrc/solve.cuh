@@ -308,13 +308,12 @@ static void setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
                        C.n_agg, C.agg_ptr.p);
         }
         // Galerkin product of the local rows
-        C.Ainv.alloc(ctx, (size_t)C.nc * C.nc);
-        C.Ainv.zero();
+        C.Ac_compact.alloc(ctx, (size_t)C.n_agg * 81);
         DevBuf<int> far(ctx, 1);
         far.zero();
         MAG_LAUNCH(ctx, coarse_galerkin_kernel, C.n_agg, 96, 0, (const uint32_t *)C.agg_ptr.p, (const uint32_t *)C.perm.p,
                    (const uint32_t *)S->Kff.rowptr.p, (const int32_t *)S->Kff.col.p, (const double *)S->Kff.val.p,
-                   (const uint32_t *)C.mode.p, (const double *)C.rot.p, S->row_lo, C.nbx, C.nby, C.nc, C.Ainv.p, far.p);
+                   (const uint32_t *)C.mode.p, (const double *)C.rot.p, S->row_lo, C.nbx, C.nby, C.nc, C.Ac_compact.p, far.p);
         int h_far = 0;
         MAG_CUDA(cudaMemcpyAsync(&h_far, far.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         MAG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -324,11 +323,15 @@ static void setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
         C.partials.alloc(ctx, 2 * (size_t)ctx->sm_count * 8);
         C.ticket.alloc(ctx, 1);
         C.ticket.zero();
-        mats.push_back(C.Ainv.p);
+        mats.push_back(C.Ac_compact.p);
     }
-    reduce_vector(ctx, ranks, m, mats, (size_t)ranks[0].S->coarse.nc * ranks[0].S->coarse.nc);
+    reduce_vector(ctx, ranks, m, mats, (size_t)ranks[0].S->coarse.n_agg * 81);      // block rows, summed over ranks
     for (RankState &W : ranks) {
         CoarseSpace &C = W.S->coarse;
+        C.Ainv.alloc(ctx, (size_t)C.nc * C.nc);
+        C.Ainv.zero();
+        MAG_LAUNCH(ctx, coarse_expand_kernel, C.n_agg, 96, 0, (const double *)C.Ac_compact.p, C.nbx, C.nby, C.nc, C.Ainv.p);
+        C.Ac_compact.release();
         MAG_LAUNCH(ctx, coarse_fix_diagonal_kernel, cdiv(C.nc, 256), 256, 0, C.Ainv.p, C.nc);
         spd_inverse(ctx, C.Ainv.p, C.nc);
         C.ready = true;
