@@ -151,7 +151,7 @@ int mag_assemble(mag_ctx *ctx, const mag_mesh *mesh, const mag_material *mat,
 /* CG on the assembled system + scatter + reactions + stress; replaces
  * solver.rs:435-482 and :578-583. */
 int mag_system_solve(mag_system *sys, const mag_options *opt, mag_result *out, mag_stats *stats);
-void mag_system_free(mag_system *sys);
+void mag_system_free(mag_system *sys);   /* multi-GPU: collective (ranks meet before exported buffers are freed) */
 int mag_system_info(const mag_system *sys, mag_stats *stats);
 
 /* parity exports (host buffers, caller-allocated from mag_system_info sizes) */

@@ -157,6 +157,19 @@ extern "C" void mag_system_free(mag_system *sys) {
         cudaSetDevice(ctx->device);
         ctx->stream = ctx->own_stream;
     }
+    // Multi-GPU: collective.  Every rank unmaps its peers' halo buffers, then all ranks meet, and only
+    // then does anyone free the buffer it exported (freeing memory another process still maps is undefined).
+    if (ctx && ctx->comm && sys->nranks > 1 && sys->shared_slab) {
+        for (void *p : sys->ipc_opened) cudaIpcCloseMemHandle(p);
+        sys->ipc_opened.clear();
+        try {
+            DevBuf<int> token(ctx, 1);
+            token.zero();
+            if (ncclAllReduce(token.p, token.p, 1, ncclInt, ncclSum, ctx->comm->nccl, ctx->stream) == ncclSuccess)
+                cudaStreamSynchronize(ctx->stream);
+        } catch (...) {
+        }
+    }
     delete sys;
     if (ctx) cudaStreamSynchronize(ctx->own_stream);
 }
