@@ -184,8 +184,11 @@ __global__ void coarse_mirror_kernel(double *__restrict__ A, uint32_t nc) {
     if (c < nc && r < c) A[(size_t)c * nc + r] = A[(size_t)r * nc + c];
 }
 
-// w = P^T r over the local rows: CTA = aggregate, fixed partition + fixed tree => deterministic
-__global__ void __launch_bounds__(128)
+// w = P^T r over the local rows: CTA = aggregate, fixed partition + fixed tree => deterministic.
+// 512 threads per aggregate: the gathers through `perm` are latency-bound, so the sequential depth
+// per thread (rows of the aggregate / 512) is what sets the time.
+constexpr int kRestrictThreads = 512;
+__global__ void __launch_bounds__(kRestrictThreads)
 coarse_restrict_kernel(const uint32_t *__restrict__ agg_ptr, const uint32_t *__restrict__ perm,
                        const uint32_t *__restrict__ mode, const double *__restrict__ rot,
                        const double *__restrict__ r, uint32_t row_lo, double *__restrict__ w,
@@ -193,14 +196,21 @@ coarse_restrict_kernel(const uint32_t *__restrict__ agg_ptr, const uint32_t *__r
     if (sc->stop) return;
     const uint32_t I = blockIdx.x;
     double a[3] = {0.0, 0.0, 0.0};
-    for (uint32_t s = agg_ptr[I] + threadIdx.x; s < agg_ptr[I + 1]; s += blockDim.x) {
-        const uint32_t gi = row_lo + perm[s];
-        const double ri = r[gi];
-        const int ax = (int)(mode[gi] % 3u);
-        a[ax] += ri;
-        a[2] = fma(rot[gi], ri, a[2]);
+    const uint32_t s1 = agg_ptr[I + 1];
+    for (uint32_t s = agg_ptr[I] + threadIdx.x; s < s1; s += 2 * kRestrictThreads) {
+        const uint32_t s2 = s + kRestrictThreads;                 // two independent gathers in flight
+        const uint32_t g0 = row_lo + perm[s], g1 = s2 < s1 ? row_lo + perm[s2] : 0u;
+        const double r0 = r[g0], r1 = s2 < s1 ? r[g1] : 0.0;
+        const uint32_t m0 = mode[g0], m1 = s2 < s1 ? mode[g1] : 0u;
+        const double t0 = rot[g0], t1 = s2 < s1 ? rot[g1] : 0.0;
+        a[m0 % 3u] += r0;
+        a[2] = fma(t0, r0, a[2]);
+        if (s2 < s1) {
+            a[m1 % 3u] += r1;
+            a[2] = fma(t1, r1, a[2]);
+        }
     }
-    __shared__ double red[3][4];
+    __shared__ double red[3][kRestrictThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -211,7 +221,10 @@ coarse_restrict_kernel(const uint32_t *__restrict__ agg_ptr, const uint32_t *__r
     __syncthreads();
     if (threadIdx.x < 3) {
         const int j = threadIdx.x;
-        w[3u * I + j] = (red[j][0] + red[j][1]) + (red[j][2] + red[j][3]);
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < kRestrictThreads / 32; ++k) s += red[j][k];
+        w[3u * I + j] = s;
     }
 }
 

@@ -210,7 +210,7 @@ static void enqueue_coarse_solve(mag_ctx *ctx, std::vector<RankState> &ranks, co
     std::vector<double *> ws;
     for (RankState &W : ranks) {
         CoarseSpace &C = W.S->coarse;
-        MAG_LAUNCH(ctx, coarse_restrict_kernel, C.n_agg, 128, 0, (const uint32_t *)C.agg_ptr.p,
+        MAG_LAUNCH(ctx, coarse_restrict_kernel, C.n_agg, kRestrictThreads, 0, (const uint32_t *)C.agg_ptr.p,
                    (const uint32_t *)C.perm.p, (const uint32_t *)C.mode.p, (const double *)C.rot.p,
                    (const double *)W.r_ext, W.S->row_lo, C.w.p, (const PcgScalars *)W.scal.p);
         ws.push_back(C.w.p);

@@ -15,16 +15,17 @@ else:
     rank, world, local = 0, 1, 0
     ctx = _lib.Context(0)
 meta = meshgen.EXAMPLE_MATERIAL
+PRECOND = int(os.environ.get("MAG_PROBE_PRECOND", "1"))
 for nx, ny in ((200, 100), (1000, 500), (2000, 1000)):
     mesh = meshgen.plate(nx, ny)
     for ar in ((0, 1) if world > 1 else (0,)):
         with solver.System(mesh, meta, ctx) as S:
             for rep in range(2):
-                sol = S.solve(_lib.default_options(allreduce=ar, max_iter=2000), allow_not_converged=True)
+                sol = S.solve(_lib.default_options(allreduce=ar, max_iter=2000, precond=PRECOND), allow_not_converged=True)
             st = sol.stats
             if rank == 0:
                 pr = ", ".join(f"{v / 1e3:.1f}" for v in st["prof"][:7])
-                print(f"tune {os.environ.get('MAG_TUNE', '0')} world {world} plate {nx}x{ny} allreduce {ar}: {st['iters']} it, "
+                print(f"precond {PRECOND} tune {os.environ.get('MAG_TUNE', '0')} world {world} plate {nx}x{ny} allreduce {ar}: {st['iters']} it, "
                       f"{1e3 * st['ms_solve'] / max(st['iters'], 1):.1f} us/it | timeline us "
                       f"[gapA, durA, gapB, waitB, durB, gapC, waitC] = [{pr}]", flush=True)
 if world > 1:
