@@ -617,6 +617,17 @@ extern "C" int mag_comm_init(mag_ctx *ctx, int rank, int nranks, const void *id1
         c->rank = rank; c->nranks = nranks;
         MAG_NCCL(ncclCommInitRank(&c->nccl, nranks, id, rank));
         ctx->comm = c.release();
+        // NCCL builds its channels on the first collective of each kind (seconds at 8 ranks): pay for that
+        // here, once per process, not inside the first solve.
+        {
+            CallScope scope(ctx, nullptr);
+            DevBuf<double> warm(ctx, (size_t)1 << 18);      // 2 MB
+            warm.zero();
+            MAG_NCCL(ncclAllReduce(warm.p, warm.p, 1, ncclDouble, ncclSum, ctx->comm->nccl, ctx->stream));
+            MAG_NCCL(ncclAllReduce(warm.p, warm.p, (size_t)1 << 18, ncclDouble, ncclSum, ctx->comm->nccl, ctx->stream));
+            MAG_NCCL(ncclBroadcast(warm.p, warm.p, (size_t)1 << 18, ncclDouble, 0, ctx->comm->nccl, ctx->stream));
+            MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
     });
 }
 

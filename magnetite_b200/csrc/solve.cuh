@@ -4,6 +4,7 @@
 // tests: same partition, same kernels, same halo stores, allreduce emulated by a
 // tiny kernel).
 #pragma once
+#include <chrono>
 #include <cmath>
 
 #include "system.cuh"
@@ -257,6 +258,15 @@ static void enqueue_iteration(mag_ctx *ctx, std::vector<RankState> &ranks, int s
 
 // Builds the aggregation coarse space of every rank's system (once per system).
 static void setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const SolveMode &m, const mag_options &opt) {
+    const bool trace = (ctx->tune & 32) != 0;          // MAG_TUNE=32: wall-clock of the setup stages on stderr
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        cudaStreamSynchronize(ctx->stream);
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[coarse setup] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     bool all_ready = true;
     for (RankState &W : ranks) all_ready = all_ready && W.S->coarse.ready;
     if (all_ready) return;
@@ -287,11 +297,13 @@ static void setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
         C.nc = 3 * C.n_agg;
         C.x0 = xmin; C.y0 = ymin;
         C.hx = Wd / C.nbx * (1.0 + 1e-12); C.hy = Hd / C.nby * (1.0 + 1e-12);
+        lap("bounding box");
         C.mode.alloc(ctx, ext_len(S)); C.rot.alloc(ctx, ext_len(S));
         C.mode.zero(); C.rot.zero();
         MAG_LAUNCH(ctx, coarse_colinfo_kernel, cdiv(n_dof, 256), 256, 0, (const double2 *)S->xy.p,
                    (const uint8_t *)S->known.p, (const uint32_t *)S->colmap.p, n_dof, C.x0, C.y0, C.hx, C.hy,
                    C.nbx, C.nby, C.mode.p, C.rot.p);
+        lap("column info");
         // local rows sorted by aggregate
         const uint32_t n = S->Kff.n_rows;
         C.perm.alloc(ctx, n);
@@ -307,6 +319,7 @@ static void setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
             MAG_LAUNCH(ctx, coarse_segments_kernel, cdiv((size_t)C.n_agg + 1, 256), 256, 0, (const uint64_t *)keys.p, n,
                        C.n_agg, C.agg_ptr.p);
         }
+        lap("sort rows by aggregate");
         // Galerkin product of the local rows
         C.Ac_compact.alloc(ctx, (size_t)C.n_agg * 81);
         DevBuf<int> far(ctx, 1);
@@ -324,8 +337,10 @@ static void setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
         C.ticket.alloc(ctx, 1);
         C.ticket.zero();
         mats.push_back(C.Ac_compact.p);
+        lap("Galerkin product");
     }
     reduce_vector(ctx, ranks, m, mats, (size_t)ranks[0].S->coarse.n_agg * 81);      // block rows, summed over ranks
+    lap("sum over ranks");
     for (RankState &W : ranks) {
         CoarseSpace &C = W.S->coarse;
         C.Ainv.alloc(ctx, (size_t)C.nc * C.nc);
@@ -335,6 +350,7 @@ static void setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
         MAG_LAUNCH(ctx, coarse_fix_diagonal_kernel, cdiv(C.nc, 256), 256, 0, C.Ainv.p, C.nc);
         spd_inverse(ctx, C.Ainv.p, C.nc);
         C.ready = true;
+        lap("expand + potrf + potri");
     }
 }
 
