@@ -106,6 +106,7 @@ extern "C" void mag_ctx_destroy(mag_ctx *ctx) {
         if (ctx->comm->nccl) ncclCommDestroy(ctx->comm->nccl);
         delete ctx->comm;
     }
+    if (ctx->cusolver) cusolver_api().destroy(ctx->cusolver);
     ctx->heap.destroy();
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

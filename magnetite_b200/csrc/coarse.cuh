@@ -292,8 +292,10 @@ inline CusolverApi &cusolver_api() {
 // In-place inverse of the SPD matrix A (nc x nc; symmetric, so row/column major coincide).
 inline void spd_inverse(mag_ctx *ctx, double *A, uint32_t nc) {
     CusolverApi &cs = cusolver_api();
-    void *h = nullptr;
-    if (cs.create(&h) != 0) fail(MAG_ERR_CUDA, "cusolverDnCreate failed");
+    // one handle per context, kept: creating it (cuBLAS initialisation, library load) costs ~0.1 s on one
+    // GPU and ~2 s when eight processes do it at once
+    if (!ctx->cusolver && cs.create(&ctx->cusolver) != 0) fail(MAG_ERR_CUDA, "cusolverDnCreate failed");
+    void *h = ctx->cusolver;
     cs.set_stream(h, ctx->stream);
     const int kLower = 0;   // CUBLAS_FILL_MODE_LOWER
     int l1 = 0, l2 = 0;
@@ -306,14 +308,12 @@ inline void spd_inverse(mag_ctx *ctx, double *A, uint32_t nc) {
     MAG_CUDA(cudaMemcpyAsync(&h_info, info.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     MAG_CUDA(cudaStreamSynchronize(ctx->stream));
     if (rc != 0 || h_info != 0) {
-        cs.destroy(h);
         fail(MAG_ERR_INDEFINITE, "coarse matrix is not positive definite (potrf info %d): the two-level "
                                  "preconditioner needs an SPD system (counter-clockwise mesh); use precond = 1", h_info);
     }
     rc = cs.potri(h, kLower, (int)nc, A, (int)nc, work.p, l2, info.p);
     MAG_CUDA(cudaMemcpyAsync(&h_info, info.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     MAG_CUDA(cudaStreamSynchronize(ctx->stream));
-    cs.destroy(h);
     if (rc != 0 || h_info != 0) fail(MAG_ERR_INDEFINITE, "potri failed (info %d)", h_info);
     // column-major LOWER == row-major UPPER: entries (r, c) with c >= r are valid; mirror to c < r
     dim3 grid(cdiv(nc, 256), nc);
