@@ -127,8 +127,4 @@ struct BsrMatrix {
     DevBuf<double> bval;                 // n_blocks*4, row-major 2x2
 };
 
-struct AssemblyTimes {
-    float ms_elem = 0, ms_sort = 0, ms_reduce = 0;
-};
-
 }  // namespace mag

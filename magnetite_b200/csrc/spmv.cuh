@@ -10,7 +10,9 @@
 //            every load instruction of the val and col streams is one fully
 //            coalesced 256 B / 128 B request.  The x gathers go through L1/L2
 //            (ld.global.nc): neighbouring rows of a mesh matrix touch
-//            neighbouring columns, so they coalesce too.
+//            neighbouring columns, so they coalesce too.  When the matrix band
+//            is < 32768 the columns are stored as 16-bit offsets from the row,
+//            two per 32-bit word (10 instead of 12 bytes per entry).
 // The SpMV that runs inside CG also produces the partial dot product p.q, so q
 // is not re-read for it.
 #pragma once
