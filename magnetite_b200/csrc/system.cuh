@@ -61,7 +61,7 @@ namespace mag {
 static void check_mesh_args(const mag_mesh *m) {
     if (!m) fail(MAG_ERR_BAD_ARG, "null mesh");
     if (m->n_nodes >= (1ull << 31)) fail(MAG_ERR_BAD_ARG, "n_nodes must be < 2^31");
-    if (m->n_elems * 9 >= (1ull << 32)) fail(MAG_ERR_BAD_ARG, "n_elems*9 must be < 2^32 per GPU");
+    if (m->n_elems >= (1ull << 32)) fail(MAG_ERR_BAD_ARG, "n_elems must be < 2^32");
     if (m->n_nodes && (!m->x || !m->y || !m->known)) fail(MAG_ERR_BAD_ARG, "mesh: x, y and known are required");
     if (m->n_elems && (!m->n0 || !m->n1 || !m->n2)) fail(MAG_ERR_BAD_ARG, "mesh: n0, n1, n2 are required");
 }
@@ -183,6 +183,8 @@ static void assemble_impl(mag_ctx *ctx, const mag_mesh *m, const mag_material *m
         elist.alloc(ctx, El);
         MAG_LAUNCH(ctx, compact_elements_kernel, cdiv(E, 256), 256, 0, (const uint32_t *)flag.p, E, elist.p);
     }
+    if ((uint64_t)El * 9 >= (1ull << 32))
+        fail(MAG_ERR_BAD_ARG, "this rank would assemble %zu elements; 9 COO keys each must stay below 2^32: use more GPUs", El);
     const uint32_t *elist_p = (nranks > 1) ? elist.p : nullptr;
     DevBuf<double> kblk(ctx, El * 36);
     if (El)
