@@ -1,0 +1,60 @@
+// magnetite_b200 — the reference's main.rs:54-76 with the numerical core on the GPU.
+//
+//   magnetite_b200 input.json geom.msh [--skip]        mesh from gmsh (or geometry.write_msh) + input.json
+//                                                      -> nodes.csv, elements.csv in the working directory
+//   magnetite_b200 --dump-rules input.json             print the parsed metadata and boundary rules (no GPU)
+//
+// The reference shells out to gmsh for the .msh (mesher.rs:501-506); that step is out of scope, so the
+// CLI starts from the mesh file.  `--skip` is accepted for compatibility (the plot step never runs here).
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "magnetite_io.hpp"
+
+using namespace magnetite;
+
+static std::string opt(const std::optional<double> &v) {
+    return v ? post_processor::format_f64(*v) : std::string("None");
+}
+
+int main(int argc, char **argv) {
+    try {
+        if (argc == 3 && !std::strcmp(argv[1], "--dump-rules")) {
+            const Json j = mesher::load_input_file(argv[2]);
+            const ModelMetadata md = mesher::parse_input_metadata(j);
+            std::printf("metadata %s %s %s %s %s\n", post_processor::format_f64(md.youngs_modulus).c_str(),
+                        post_processor::format_f64(md.poisson_ratio).c_str(), post_processor::format_f64(md.part_thickness).c_str(),
+                        post_processor::format_f64(md.characteristic_length_min).c_str(),
+                        post_processor::format_f64(md.characteristic_length_max).c_str());
+            for (const BoundaryRule &r : mesher::parse_boundary_rules(j))
+                std::printf("rule %s region %s %s %s %s targets %s %s %s %s\n", r.name.c_str(),
+                            post_processor::format_f64(r.region.x_min).c_str(), post_processor::format_f64(r.region.x_max).c_str(),
+                            post_processor::format_f64(r.region.y_min).c_str(), post_processor::format_f64(r.region.y_max).c_str(),
+                            opt(r.target.ux).c_str(), opt(r.target.uy).c_str(), opt(r.target.fx).c_str(), opt(r.target.fy).c_str());
+            return 0;
+        }
+        if (argc < 3) {
+            std::fprintf(stderr, "usage: magnetite_b200 input.json geom.msh [--skip]\n");
+            return 2;
+        }
+        const std::string input_file = argv[1], mesh_file = argv[2];
+        if (mesh_file.size() < 4 || mesh_file.substr(mesh_file.size() - 4) != ".msh")
+            throw MagnetiteError(MagnetiteError::Kind::Input,
+                                 "Unrecognized geometry filetype " + mesh_file + " (run gmsh on the outline first and pass the .msh)");
+        const Json j = mesher::load_input_file(input_file);                     // mesher.rs:943-944
+        const ModelMetadata md = mesher::parse_input_metadata(j);
+        std::vector<Node> nodes;
+        std::vector<Element> elements;
+        mesher::parse_mesh(mesh_file, nodes, elements);                          // mesher.rs:969
+        mesher::check_ccw(elements, solver::element_areas(elements, nodes));     // mesher.rs:691-693
+        std::printf("info: loaded %zu nodes and %zu elements\n", nodes.size(), elements.size());
+        mesher::apply_boundary_conditions(j, nodes, false);                      // mesher.rs:971
+        solver::run(nodes, elements, md);                                        // main.rs:64
+        post_processor::csv_output(elements, nodes, "nodes.csv", "elements.csv");   // main.rs:67-69
+    } catch (const MagnetiteError &err) {
+        std::fprintf(stderr, "Received error: %s\n", err.what());                // main.rs:46
+        return 1;
+    }
+    return 0;
+}

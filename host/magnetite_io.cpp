@@ -1,0 +1,277 @@
+// magnetite_io.cpp — see magnetite_io.hpp.
+#include "magnetite_io.hpp"
+
+#include <cctype>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <limits>
+#include <sstream>
+
+#include "../include/magnetite_b200.h"
+
+namespace magnetite {
+
+using Kind = MagnetiteError::Kind;
+
+// ---------------------------------------------------------------------------
+// JSON
+// ---------------------------------------------------------------------------
+namespace {
+struct Parser {
+    const std::string &s;
+    size_t i = 0;
+    explicit Parser(const std::string &t) : s(t) {}
+    [[noreturn]] void bad(const std::string &why) const {
+        throw MagnetiteError(Kind::Input, "Error in input file json: " + why + " at offset " + std::to_string(i));
+    }
+    void ws() { while (i < s.size() && std::isspace((unsigned char)s[i])) ++i; }
+    bool eat(char c) { ws(); if (i < s.size() && s[i] == c) { ++i; return true; } return false; }
+    std::string str() {
+        if (!eat('"')) bad("expected a string");
+        std::string out;
+        while (i < s.size() && s[i] != '"') {
+            if (s[i] == '\\' && i + 1 < s.size()) {
+                const char e = s[++i];
+                out += (e == 'n') ? '\n' : (e == 't') ? '\t' : e;
+            } else {
+                out += s[i];
+            }
+            ++i;
+        }
+        if (i >= s.size()) bad("unterminated string");
+        ++i;
+        return out;
+    }
+    Json value() {
+        ws();
+        if (i >= s.size()) bad("unexpected end");
+        Json v;
+        const char c = s[i];
+        if (c == '{') {
+            ++i; v.type = Json::Type::Object;
+            if (eat('}')) return v;
+            do {
+                std::string k = str();
+                if (!eat(':')) bad("expected ':'");
+                v.object.emplace_back(std::move(k), value());
+            } while (eat(','));
+            if (!eat('}')) bad("expected '}'");
+        } else if (c == '[') {
+            ++i; v.type = Json::Type::Array;
+            if (eat(']')) return v;
+            do v.array.push_back(value()); while (eat(','));
+            if (!eat(']')) bad("expected ']'");
+        } else if (c == '"') {
+            v.type = Json::Type::String; v.string = str();
+        } else if (s.compare(i, 4, "null") == 0) {
+            i += 4;
+        } else if (s.compare(i, 4, "true") == 0) {
+            i += 4; v.type = Json::Type::Bool; v.boolean = true;
+        } else if (s.compare(i, 5, "false") == 0) {
+            i += 5; v.type = Json::Type::Bool;
+        } else {
+            char *end = nullptr;
+            v.number = std::strtod(s.c_str() + i, &end);
+            if (end == s.c_str() + i) bad("unexpected character");
+            i = (size_t)(end - s.c_str());
+            v.type = Json::Type::Number;
+        }
+        return v;
+    }
+};
+const Json kNull;
+}  // namespace
+
+Json Json::parse(const std::string &text) {
+    Parser p(text);
+    Json v = p.value();
+    p.ws();
+    if (p.i != text.size()) p.bad("trailing characters");
+    return v;
+}
+bool Json::has_key(const std::string &k) const {
+    for (const auto &kv : object) if (kv.first == k) return true;
+    return false;
+}
+const Json &Json::operator[](const std::string &k) const {
+    for (const auto &kv : object) if (kv.first == k) return kv.second;
+    return kNull;
+}
+std::optional<double> Json::as_f64() const {
+    if (type == Type::Number) return number;
+    return std::nullopt;
+}
+
+// ---------------------------------------------------------------------------
+// mesher
+// ---------------------------------------------------------------------------
+namespace mesher {
+
+Json load_input_file(const std::string &input_file) {          // mesher.rs:713-760
+    std::ifstream f(input_file);
+    if (!f) throw MagnetiteError(Kind::Input, "Unable to open input file " + input_file);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    Json j = Json::parse(ss.str());
+    if (!j.has_key("metadata")) throw MagnetiteError(Kind::Input, "Input json missing metadata field");
+    if (!j.has_key("boundary_conditions"))
+        throw MagnetiteError(Kind::Input, "Input json missing boundary_conditions field in metadata section");
+    for (const char *k : {"part_thickness", "material_elasticity", "poisson_ratio"})
+        if (!j["metadata"].has_key(k))
+            throw MagnetiteError(Kind::Input, std::string("Input json missing ") + k + " field in metadata section");
+    return j;
+}
+
+ModelMetadata parse_input_metadata(const Json &j) {             // mesher.rs:769-808
+    const Json &md = j["metadata"];
+    const auto e = md["material_elasticity"].as_f64(), t = md["part_thickness"].as_f64();
+    const auto nu = md["poisson_ratio"].as_f64();
+    const auto cmin = md["characteristic_length_min"].as_f64(), cmax = md["characteristic_length_max"].as_f64();
+    if (!e) throw MagnetiteError(Kind::Input, "Input json missing material elasticity");
+    if (!nu) throw MagnetiteError(Kind::Input, "Input json missing poisson ratio");
+    if (!cmin) throw MagnetiteError(Kind::Input, "Input json missing minimum characteristic length");
+    if (!cmax) throw MagnetiteError(Kind::Input, "Input json missing maximum characteristic length");
+    if (!t) throw MagnetiteError(Kind::Input, "Input json missing part thickness");     // the reference unwrap()s
+    return ModelMetadata{*e, *nu, *t, (float)*cmin, (float)*cmax};
+}
+
+std::vector<BoundaryRule> parse_boundary_rules(const Json &j) { // mesher.rs:822-903
+    std::vector<BoundaryRule> rules;
+    constexpr double lo = std::numeric_limits<double>::lowest(), hi = std::numeric_limits<double>::max();
+    for (const auto &kv : j["boundary_conditions"].object) {
+        const std::string &name = kv.first;
+        const Json &rule = kv.second;
+        if (!rule.has_key("region")) throw MagnetiteError(Kind::Input, "Boundary rule " + name + " is missing region field");
+        if (!rule.has_key("targets")) throw MagnetiteError(Kind::Input, "Boundary rule " + name + " is missing target field");
+        BoundaryRegion reg{lo, hi, lo, hi};
+        const Json &r = rule["region"];
+        auto bound = [&](const char *key, double &dst) {
+            if (!r.has_key(key)) return;
+            const auto v = r[key].as_f64();
+            if (!v) throw MagnetiteError(Kind::Input, std::string("Bad value for ") + key + " in " + name);
+            dst = *v;
+        };
+        bound("x_target_min", reg.x_min); bound("x_target_max", reg.x_max);
+        bound("y_target_min", reg.y_min); bound("y_target_max", reg.y_max);
+        const Json &tg = rule["targets"];
+        BoundaryTarget t{tg["ux"].as_f64(), tg["uy"].as_f64(), tg["fx"].as_f64(), tg["fy"].as_f64()};
+        if (reg.x_min > reg.x_max) throw MagnetiteError(Kind::Input, "Boundary '" + name + "' has x_target_min greater than x_target_max");
+        if (reg.y_min > reg.y_max) throw MagnetiteError(Kind::Input, "Boundary '" + name + "' has y_target_min greater than y_target_max");
+        if (!t.fx && !t.ux) throw MagnetiteError(Kind::Input, "Boundary '" + name + "' is under-constrained in x-axis");
+        if (!t.fy && !t.uy) throw MagnetiteError(Kind::Input, "Boundary '" + name + "' is under-constrained in y-axis");
+        if (t.fx && t.ux) throw MagnetiteError(Kind::Input, "Boundary '" + name + "' is over-constrained in x-axis");
+        if (t.fy && t.uy) throw MagnetiteError(Kind::Input, "Boundary '" + name + "' is over-constrained in y-axis");
+        rules.push_back(BoundaryRule{name, reg, t});
+    }
+    return rules;
+}
+
+void apply_boundary_conditions(const Json &j, std::vector<Node> &nodes, bool quiet) {   // mesher.rs:905-927
+    const std::vector<BoundaryRule> rules = parse_boundary_rules(j);
+    if (!quiet) std::printf("info: loaded %zu boundary rules from input file\n", rules.size());
+    for (Node &n : nodes)
+        for (const BoundaryRule &r : rules)
+            if (n.vertex.x > r.region.x_min && n.vertex.x < r.region.x_max && n.vertex.y > r.region.y_min &&
+                n.vertex.y < r.region.y_max) {
+                n.ux = r.target.ux; n.uy = r.target.uy; n.fx = r.target.fx; n.fy = r.target.fy;
+            }
+}
+
+void parse_mesh(const std::string &mesh_file, std::vector<Node> &nodes, std::vector<Element> &elements) {
+    std::ifstream f(mesh_file);                                  // mesher.rs:536-704 (file kept, no check_ccw)
+    if (!f) throw MagnetiteError(Kind::Mesher, "Unable to open auto-generated mesh file: " + mesh_file);
+    enum { Limbo, Entities, Nodes, Elements } state = Limbo;
+    bool seen_meta = false;
+    std::vector<Node> unordered;
+    std::vector<size_t> indexes;
+    elements.clear();
+    std::string line;
+    auto ints = [](const std::string &l) {
+        std::vector<long long> v; std::stringstream ss(l); long long x;
+        while (ss >> x) v.push_back(x);
+        return v;
+    };
+    while (std::getline(f, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line.empty()) continue;
+        if (line.rfind("$End", 0) == 0) state = Limbo;
+        if (state == Limbo) {
+            seen_meta = false;
+            if (line.rfind("$Entities", 0) == 0) state = Entities;
+            else if (line.rfind("$Node", 0) == 0) state = Nodes;
+            else if (line.rfind("$Elements", 0) == 0) state = Elements;
+            continue;
+        }
+        if (state == Nodes) {
+            if (!seen_meta) { seen_meta = true; continue; }
+            const auto head = ints(line);
+            if (head.size() < 4) throw MagnetiteError(Kind::Mesher, "Unexpected non-int in mesh data");
+            const size_t n_local = (size_t)head[3];
+            std::vector<size_t> tags(n_local);
+            for (size_t k = 0; k < n_local; ++k) { std::getline(f, line); tags[k] = (size_t)std::stoull(line); }
+            for (size_t k = 0; k < n_local; ++k) {
+                std::getline(f, line);
+                std::stringstream ss(line);
+                double x = 0, y = 0; ss >> x >> y;
+                unordered.push_back(Node{{x, y}, std::nullopt, std::nullopt, 0.0, 0.0});   // mesher.rs:615-624
+                indexes.push_back(tags[k] - 1);
+            }
+        } else if (state == Elements) {
+            if (!seen_meta) { seen_meta = true; continue; }
+            const auto head = ints(line);
+            if (head.size() < 4) throw MagnetiteError(Kind::Mesher, "Unexpected non-int in mesh data");
+            const long long entity_dim = head[0];
+            for (long long k = 0; k < head[3]; ++k) {
+                std::getline(f, line);
+                const auto meta = ints(line);
+                if (entity_dim != 2) continue;
+                if (meta.size() < 4) throw MagnetiteError(Kind::Mesher, "Unexpected non-int in mesh data");
+                elements.push_back(Element{{(size_t)meta[1] - 1, (size_t)meta[2] - 1, (size_t)meta[3] - 1}, std::nullopt});
+            }
+        }
+    }
+    nodes.assign(unordered.size(), Node{{0, 0}, std::nullopt, std::nullopt, std::nullopt, std::nullopt});
+    std::vector<char> seen(unordered.size(), 0);
+    for (size_t k = 0; k < unordered.size(); ++k) {
+        if (indexes[k] >= nodes.size()) throw MagnetiteError(Kind::Mesher, "node tags are not dense 1..N");
+        nodes[indexes[k]] = unordered[k];
+        seen[indexes[k]] = 1;
+    }
+    for (char s : seen) if (!s) throw MagnetiteError(Kind::Mesher, "node tags are not dense 1..N");
+}
+
+void check_ccw(std::vector<Element> &elements, const std::vector<double> &areas) {     // mesher.rs:522-526
+    for (size_t e = 0; e < elements.size(); ++e)
+        if (areas[e] < 1.0) std::swap(elements[e].nodes[0], elements[e].nodes[2]);
+}
+
+}  // namespace mesher
+
+namespace solver {
+std::vector<double> element_areas(const std::vector<Element> &elements, const std::vector<Node> &nodes, int device) {
+    const size_t n = nodes.size(), e = elements.size();
+    std::vector<double> x(n), y(n), area(e);
+    std::vector<std::uint8_t> known(n, 0);
+    std::vector<std::uint32_t> n0(e), n1(e), n2(e);
+    for (size_t i = 0; i < n; ++i) { x[i] = nodes[i].vertex.x; y[i] = nodes[i].vertex.y; }
+    for (size_t i = 0; i < e; ++i) {
+        n0[i] = (std::uint32_t)elements[i].nodes[0]; n1[i] = (std::uint32_t)elements[i].nodes[1];
+        n2[i] = (std::uint32_t)elements[i].nodes[2];
+    }
+    mag_mesh m{};
+    m.n_nodes = n; m.n_elems = e; m.x = x.data(); m.y = y.data();
+    m.n0 = n0.data(); m.n1 = n1.data(); m.n2 = n2.data(); m.known = known.data();
+    mag_ctx *ctx = nullptr;
+    int rc = mag_ctx_create(&ctx, device);
+    if (rc != MAG_OK) throw MagnetiteError(Kind::Solver, mag_last_error(), rc);
+    rc = mag_element_area(ctx, &m, area.data());
+    const std::string msg = rc != MAG_OK ? mag_last_error() : "";
+    mag_ctx_destroy(ctx);
+    if (rc != MAG_OK) throw MagnetiteError(Kind::Solver, msg, rc);
+    return area;
+}
+}  // namespace solver
+
+}  // namespace magnetite

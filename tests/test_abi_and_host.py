@@ -173,3 +173,26 @@ def test_stress_strain_matrix_matches_oracle(built):
     from oracle import oracle as O
     for nu, E in ((0.33, 69e9), (0.25, 210e9), (0.0, 1.0), (0.49, 3e6)):
         assert np.array_equal(solver.compute_stress_strain_matrix(nu, E), O.stress_strain(nu, E))
+
+
+def test_cpp_cli_parses_input_json_like_the_python_mirror(built):
+    """host/magnetite_b200 --dump-rules: the C++ mirror of load_input_file / parse_input_metadata /
+    parse_boundary_rules agrees with magnetite_b200.mesher on the tensile example (no GPU needed)."""
+    import subprocess
+    subprocess.run(["make", "-C", str(ROOT / "host")], check=True, capture_output=True)
+    path = str(GOLDEN / "tensile_input.json")
+    r = subprocess.run([str(ROOT / "host" / "magnetite_b200"), "--dump-rules", path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    f = post_processor.rust_f64_display
+    data = mesher.load_input_file(path)
+    meta = mesher.parse_input_metadata(data)
+    want = [f"metadata {f(meta.youngs_modulus)} {f(meta.poisson_ratio)} {f(meta.part_thickness)} "
+            f"{f(meta.characteristic_length_min)} {f(meta.characteristic_length_max)}"]
+    o = lambda v: "None" if v is None else f(v)
+    for rule in mesher.parse_boundary_rules(data):
+        g, tg = rule.region, rule.target
+        want.append(f"rule {rule.name} region {f(g.x_min)} {f(g.x_max)} {f(g.y_min)} {f(g.y_max)} "
+                    f"targets {o(tg.ux)} {o(tg.uy)} {o(tg.fx)} {o(tg.fy)}")
+    assert r.stdout.splitlines() == want
+    bad = subprocess.run([str(ROOT / "host" / "magnetite_b200"), path, "outline.svg"], capture_output=True, text=True)
+    assert bad.returncode == 1 and "Received error: Input error: Unrecognized geometry filetype" in bad.stderr

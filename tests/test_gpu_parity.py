@@ -531,3 +531,33 @@ def test_compat_returns_best_param_when_max_iters_ends_the_run(ctx, max_iter):
     ur = np.concatenate([ref["ux"], ref["uy"]])
     assert rel_l2(np.concatenate([sol.ux, sol.uy]), ur) < 1e-9
     assert abs(sol.stats["final_residual"] - ref["stats"]["final_cost"]) <= 1e-9 * ref["stats"]["final_cost"]
+
+
+def test_cpp_cli_full_flow_matches_python_flow(ctx, tmp_path):
+    """main.rs:54-76 in C++ (parse_mesh -> check_ccw -> apply_boundary_conditions -> solver::run ->
+    csv_output) against the same flow through the Python mirror: byte-identical CSVs.  The mesh has
+    triangles of area 0.5, so check_ccw flips every element (the tensile-example quirk)."""
+    import subprocess
+    from magnetite_b200 import geometry, mesher, post_processor
+    root = Path(__file__).resolve().parent.parent
+    subprocess.run(["make", "-C", str(root / "host")], check=True, capture_output=True)
+    m = meshgen.jitter(meshgen.plate(22, 9, h=1.0), frac=0.1)
+    xs = m.x - 11.0
+    conn = np.stack([m.n0, m.n1, m.n2], 1).astype(int)
+    geometry.write_msh(str(tmp_path / "geom.msh"), xs, m.y, conn)
+    inp = str(GOLDEN / "tensile_input.json")
+    r = subprocess.run([str(root / "host" / "magnetite_b200"), inp, "geom.msh", "--skip"], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "info: loaded 230 nodes and 396 elements" in r.stdout and "info: loaded 2 boundary rules" in r.stdout
+    # the same flow through the Python mirror
+    nodes, elements = geometry.parse_mesh(str(tmp_path / "geom.msh"))
+    mesher.check_ccw(elements, nodes)
+    assert all(e.nodes != list(c) for e, c in zip(elements, conn))          # every element was flipped
+    data = mesher.load_input_file(inp)
+    mesher.apply_boundary_conditions(data, nodes)
+    solver.run(nodes, elements, mesher.parse_input_metadata(data), quiet=True)
+    post_processor.csv_output(elements, nodes, str(tmp_path / "n_py.csv"), str(tmp_path / "e_py.csv"), quiet=True)
+    assert (tmp_path / "nodes.csv").read_bytes() == (tmp_path / "n_py.csv").read_bytes()
+    assert (tmp_path / "elements.csv").read_bytes() == (tmp_path / "e_py.csv").read_bytes()
+    assert max(n.ux for n in nodes) == 3.0 and min(n.ux for n in nodes) == 0.0
