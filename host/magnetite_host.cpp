@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 
 #include "../include/magnetite_b200.h"
@@ -137,9 +138,26 @@ namespace post_processor {
 std::string format_f64(double v) {
     if (std::isnan(v)) return "NaN";
     if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
-    char buf[400];
-    const auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);   // shortest round trip
-    return std::string(buf, r.ptr);
+    // Rust prints the SHORTEST round-trip digits and pads with zeros (1.2345678901234567e25 ->
+    // "12345678901234567000000000"); to_chars(fixed) would print the exact binary expansion instead,
+    // so take the shortest digits from the scientific form and place the point by hand.
+    char buf[64];
+    const auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);
+    std::string s(buf, r.ptr), out;
+    if (s[0] == '-') { out = "-"; s.erase(0, 1); }
+    const size_t epos = s.find('e');
+    const int exp10 = std::atoi(s.c_str() + epos + 1);
+    std::string digits;
+    for (size_t i = 0; i < epos; ++i) if (s[i] != '.') digits += s[i];
+    const int n = (int)digits.size();
+    if (exp10 >= n - 1) {
+        out += digits + std::string((size_t)(exp10 - (n - 1)), '0');
+    } else if (exp10 >= 0) {
+        out += digits.substr(0, (size_t)exp10 + 1) + "." + digits.substr((size_t)exp10 + 1);
+    } else {
+        out += "0." + std::string((size_t)(-exp10 - 1), '0') + digits;
+    }
+    return out;
 }
 
 void csv_output(const std::vector<Element> &elements, const std::vector<Node> &nodes,

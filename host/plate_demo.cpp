@@ -11,14 +11,15 @@
 using namespace magnetite;
 
 static int format_selftest() {
-    struct { double v; const char *s; } cases[] = {
+    struct { double v; std::string s; } cases[] = {
         {3.0, "3"}, {-0.0, "-0"}, {0.0, "0"}, {69e9, "69000000000"}, {1e-7, "0.0000001"},
         {0.1 + 0.2, "0.30000000000000004"}, {-4.5, "-4.5"}, {1e21, "1000000000000000000000"},
-        {1.5e-10, "0.00000000015"}};
+        {1.5e-10, "0.00000000015"}, {1.2345678901234567e25, "12345678901234566000000000"}, {123456.789, "123456.789"},
+        {-2.5e-5, "-0.000025"}, {1e15, "1000000000000000"}, {5e-324, "0." + std::string(323, '0') + "5"}};
     int bad = 0;
     for (auto &c : cases) {
         const std::string got = post_processor::format_f64(c.v);
-        if (got != c.s) { std::printf("MISMATCH %.17g -> %s (want %s)\n", c.v, got.c_str(), c.s); ++bad; }
+        if (got != c.s) { std::printf("MISMATCH %.17g -> %s (want %s)\n", c.v, got.c_str(), c.s.c_str()); ++bad; }
     }
     MagnetiteError e(MagnetiteError::Kind::PostProcessor, "x");
     if (std::string(e.what()) != "Post Processor error: x") ++bad;

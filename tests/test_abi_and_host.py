@@ -88,6 +88,7 @@ def test_rust_display_formatting():
     assert f(69e9) == "69000000000" and f(1e-7) == "0.0000001"
     assert f(0.1 + 0.2) == "0.30000000000000004" and f(-4.5) == "-4.5"
     assert f(1e21) == "1000000000000000000000" and f(1.5e-10) == "0.00000000015"
+    assert f(1.2345678901234567e25) == "12345678901234566000000000"      # shortest digits, zero padded (not the exact expansion)
     assert f(float("nan")) == "NaN" and f(float("inf")) == "inf" and f(float("-inf")) == "-inf"
     for v in np.random.default_rng(0).normal(size=200) * 10.0 ** np.random.default_rng(1).integers(-12, 12, 200):
         assert float(f(v)) == v and "e" not in f(v)
