@@ -66,8 +66,9 @@ __global__ void band_width_kernel(const uint32_t *__restrict__ rowptr, const int
     if ((threadIdx.x & 31) == 0 && b) atomicMax(band, b);
 }
 
-// Wide: scol[base + k*32 + lane] = absolute column.  Narrow: the slice width is even and
-// pcol[base/2 + (k/2)*32 + lane] packs the 16-bit offsets (column - global row) of entries k and k+1.
+// Wide: sval/scol[base + k*32 + lane] = value / absolute column of entry k.  Narrow: the slice width is
+// even; pcol[base/2 + (k/2)*32 + lane] packs the 16-bit offsets (column - global row) of entries k and
+// k+1, and their two values sit next to each other at sval[2*(base/2 + (k/2)*32 + lane) + {0,1}].
 template <bool NARROW>
 __global__ void sell_fill_kernel(const uint32_t *__restrict__ rowptr, const int32_t *__restrict__ ccol,
                                  const double *__restrict__ cval, uint32_t n_rows, uint32_t row_lo,
@@ -89,7 +90,9 @@ __global__ void sell_fill_kernel(const uint32_t *__restrict__ rowptr, const int3
     for (uint32_t k = 0; k < w; ++k) {
         const bool real = k < len;
         const int32_t c = real ? ccol[p0 + k] : grow;
-        sval[base + (size_t)k * 32] = real ? cval[p0 + k] : 0.0;
+        // narrow: values travel in pairs too (entries k, k+1 of a lane are adjacent: one 16-byte load)
+        const size_t vpos = NARROW ? (pbase + (size_t)(k >> 1) * 32) * 2 + (k & 1u) : base + (size_t)k * 32;
+        sval[vpos] = real ? cval[p0 + k] : 0.0;
         if (NARROW) {
             const uint32_t d = (uint32_t)(uint16_t)(int16_t)(c - grow);
             if (k & 1u) pcol[pbase + (size_t)(k >> 1) * 32] = pack | (d << 16);
@@ -263,23 +266,35 @@ __device__ __forceinline__ double sell_rows(const uint32_t *__restrict__ slice_o
         uint32_t k = 0;
         IdxBatch<IDX> cur, nxt;
         if (w >= 4) nxt.load(c, 0);
-        for (; k + 4 <= w; k += 4) {
-            cur = nxt;
-            if (k + 8 <= w) nxt.load(c, k + 4);                 // next batch's indices, in flight early
-            const double a0 = __ldcs(v + (size_t)(k + 0) * 32), a1 = __ldcs(v + (size_t)(k + 1) * 32);
-            const double a2 = __ldcs(v + (size_t)(k + 2) * 32), a3 = __ldcs(v + (size_t)(k + 3) * 32);
-            const double x0 = __ldg(xb + cur.o0()), x1 = __ldg(xb + cur.o1());
-            const double x2 = __ldg(xb + cur.o2()), x3 = __ldg(xb + cur.o3());
-            acc0 = fma(a0, x0, acc0); acc1 = fma(a1, x1, acc1);
-            acc0 = fma(a2, x2, acc0); acc1 = fma(a3, x3, acc1);
-        }
-        if (kNarrow) {
+        if constexpr (kNarrow) {
+            // vectorised value stream: one 16-byte load per lane covers two entries (512 B per warp request)
+            const double2 *v2 = reinterpret_cast<const double2 *>(sval) + (size_t)o0 * 16 + lane;
+            for (; k + 4 <= w; k += 4) {
+                cur = nxt;
+                if (k + 8 <= w) nxt.load(c, k + 4);             // next batch's indices, in flight early
+                const double2 a01 = __ldcs(v2 + (size_t)(k >> 1) * 32), a23 = __ldcs(v2 + (size_t)((k >> 1) + 1) * 32);
+                const double x0 = __ldg(xb + cur.o0()), x1 = __ldg(xb + cur.o1());
+                const double x2 = __ldg(xb + cur.o2()), x3 = __ldg(xb + cur.o3());
+                acc0 = fma(a01.x, x0, acc0); acc1 = fma(a01.y, x1, acc1);
+                acc0 = fma(a23.x, x2, acc0); acc1 = fma(a23.y, x3, acc1);
+            }
             for (; k < w; k += 2) {        // w is even in narrow mode
                 const uint32_t p0 = __ldcs(reinterpret_cast<const uint32_t *>(c) + (size_t)(k >> 1) * 32);
-                acc0 = fma(__ldcs(v + (size_t)k * 32), __ldg(xb + (int)(short)(p0 & 0xffffu)), acc0);
-                acc1 = fma(__ldcs(v + (size_t)(k + 1) * 32), __ldg(xb + ((int)p0 >> 16)), acc1);
+                const double2 a01 = __ldcs(v2 + (size_t)(k >> 1) * 32);
+                acc0 = fma(a01.x, __ldg(xb + (int)(short)(p0 & 0xffffu)), acc0);
+                acc1 = fma(a01.y, __ldg(xb + ((int)p0 >> 16)), acc1);
             }
         } else {
+            for (; k + 4 <= w; k += 4) {
+                cur = nxt;
+                if (k + 8 <= w) nxt.load(c, k + 4);             // next batch's indices, in flight early
+                const double a0 = __ldcs(v + (size_t)(k + 0) * 32), a1 = __ldcs(v + (size_t)(k + 1) * 32);
+                const double a2 = __ldcs(v + (size_t)(k + 2) * 32), a3 = __ldcs(v + (size_t)(k + 3) * 32);
+                const double x0 = __ldg(xb + cur.o0()), x1 = __ldg(xb + cur.o1());
+                const double x2 = __ldg(xb + cur.o2()), x3 = __ldg(xb + cur.o3());
+                acc0 = fma(a0, x0, acc0); acc1 = fma(a1, x1, acc1);
+                acc0 = fma(a2, x2, acc0); acc1 = fma(a3, x3, acc1);
+            }
             for (; k < w; ++k)
                 acc0 = fma(__ldcs(v + (size_t)k * 32), __ldg(xb + (int)__ldcs(reinterpret_cast<const int32_t *>(c) + (size_t)k * 32)), acc0);
         }
