@@ -176,6 +176,15 @@ int mag_system_spmv(mag_system *sys, int format, const double *x, double *y);
 int mag_system_spmv_bench(mag_system *sys, int format, int reps, float *ms_per_spmv,
                           uint64_t *algorithmic_bytes);
 
+/* ---- output stage: post_processor::csv_output (src/post_processor.rs:18-83), host only ---------
+ * nodes.csv "x,y,ux,uy", elements.csv "n0,n1,n2,stress", "\n" line ends, f64 printed like Rust's `{}`
+ * (shortest round-trip digits, never scientific, no ".0").  Buffered.  Errors: mag_csv_last_error(). */
+int mag_csv_output(const char *nodes_path, const char *elements_path, uint64_t n_nodes, const double *x,
+                   const double *y, const double *ux, const double *uy, uint64_t n_elems,
+                   const uint32_t *n0, const uint32_t *n1, const uint32_t *n2, const double *stress);
+size_t mag_format_f64(double v, char *out /* >= 400 bytes, NUL-terminated */);
+const char *mag_csv_last_error(void);
+
 /* ---- synthetic meshes generated on the device ------------- */
 /* Plate(nx,ny,h): node (i,j) -> id j*(nx+1)+i at (i*h, j*h); cell -> [a,b,d],[a,d,c];
  * left edge clamped, right edge ux=ux_right, fy=0.  All outputs are device

@@ -28,8 +28,23 @@ def rust_f64_display(v: float) -> str:
     return np.format_float_positional(v, unique=True, trim="-")
 
 
+def write_csv_fast(x, y, ux, uy, n0, n1, n2, stress, nodes_output: str, elements_output: str) -> None:
+    """The same files through the library's host-side writer (mag_csv_output, csrc/csv.cpp): tens of
+    millions of rows per minute instead of Python string formatting."""
+    from . import _lib
+    c = np.ascontiguousarray
+    x, y, ux, uy, stress = (c(a, np.float64) for a in (x, y, ux, uy, stress))
+    n0, n1, n2 = (c(a, np.uint32) for a in (n0, n1, n2))
+    lib = _lib.load()
+    rc = lib.mag_csv_output(nodes_output.encode(), elements_output.encode(), x.shape[0], _lib.ptr(x), _lib.ptr(y),
+                            _lib.ptr(ux), _lib.ptr(uy), n0.shape[0], _lib.ptr(n0), _lib.ptr(n1), _lib.ptr(n2),
+                            _lib.ptr(stress))
+    if rc != 0:
+        raise MagnetiteError.Solver((lib.mag_csv_last_error() or b"").decode(), code=rc)
+
+
 def write_csv_arrays(x, y, ux, uy, n0, n1, n2, stress, nodes_output: str, elements_output: str) -> None:
-    """Array-level writer (buffered; the reference issues one unbuffered write per row)."""
+    """Array-level writer in pure Python (buffered; the reference issues one unbuffered write per row)."""
     try:
         nf = open(nodes_output, "w", newline="")
     except OSError as err:                                   # post_processor.rs:24-31

@@ -197,3 +197,27 @@ def test_cpp_cli_parses_input_json_like_the_python_mirror(built):
     assert r.stdout.splitlines() == want
     bad = subprocess.run([str(ROOT / "host" / "magnetite_b200"), path, "outline.svg"], capture_output=True, text=True)
     assert bad.returncode == 1 and "Received error: Input error: Unrecognized geometry filetype" in bad.stderr
+
+
+def test_library_csv_writer_matches_python_writer(tmp_path, built):
+    """mag_csv_output (host-only code in the library) writes byte-identical files to the Python writer,
+    including awkward floats; mag_format_f64 agrees with the Rust-style formatter on random values."""
+    import ctypes as C
+    rng = np.random.default_rng(11)
+    n, e = 2000, 3000
+    mag = 10.0 ** rng.integers(-14, 14, n)
+    x = rng.normal(size=n) * mag; y = np.round(rng.normal(size=n) * 10) ; ux = rng.normal(size=n) * 1e-3
+    uy = np.where(rng.random(n) < 0.1, 0.0, rng.normal(size=n)); uy[:3] = [-0.0, 3.0, 1e-7]
+    n0, n1, n2 = (rng.integers(0, n, e).astype(np.uint32) for _ in range(3))
+    stress = rng.normal(size=e) * 1e8; stress[:4] = [float("nan"), float("inf"), -float("inf"), 69e9]
+    post_processor.write_csv_arrays(x, y, ux, uy, n0, n1, n2, stress, str(tmp_path / "n_py.csv"), str(tmp_path / "e_py.csv"))
+    post_processor.write_csv_fast(x, y, ux, uy, n0, n1, n2, stress, str(tmp_path / "n_c.csv"), str(tmp_path / "e_c.csv"))
+    assert (tmp_path / "n_py.csv").read_bytes() == (tmp_path / "n_c.csv").read_bytes()
+    assert (tmp_path / "e_py.csv").read_bytes() == (tmp_path / "e_c.csv").read_bytes()
+    lib = _lib.load()
+    buf = C.create_string_buffer(512)
+    for v in list(rng.normal(size=300) * 10.0 ** rng.integers(-300, 300, 300)) + [5e-324, 1.7976931348623157e308, -0.0]:
+        lib.mag_format_f64(float(v), buf)
+        assert buf.value.decode() == post_processor.rust_f64_display(v)
+    with pytest.raises(MagnetiteError, match="Failed to create nodes.csv"):
+        post_processor.write_csv_fast(x, y, ux, uy, n0, n1, n2, stress, str(tmp_path / "no" / "n.csv"), str(tmp_path / "e.csv"))
