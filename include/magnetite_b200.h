@@ -178,12 +178,27 @@ int mag_system_spmv_bench(mag_system *sys, int format, int reps, float *ms_per_s
 
 /* ---- output stage: post_processor::csv_output (src/post_processor.rs:18-83), host only ---------
  * nodes.csv "x,y,ux,uy", elements.csv "n0,n1,n2,stress", "\n" line ends, f64 printed like Rust's `{}`
- * (shortest round-trip digits, never scientific, no ".0").  Buffered.  Errors: mag_csv_last_error(). */
+ * (shortest round-trip digits, never scientific, no ".0").  Buffered.  Errors: mag_host_last_error(). */
 int mag_csv_output(const char *nodes_path, const char *elements_path, uint64_t n_nodes, const double *x,
                    const double *y, const double *ux, const double *uy, uint64_t n_elems,
                    const uint32_t *n0, const uint32_t *n1, const uint32_t *n2, const double *stress);
 size_t mag_format_f64(double v, char *out /* >= 400 bytes, NUL-terminated */);
-const char *mag_csv_last_error(void);
+/* message of the last failed HOST-ONLY entry point on this thread (mag_csv_output, mag_reorder_rcm,
+ * mag_mesh_band); the device entry points report through mag_last_error(). */
+const char *mag_host_last_error(void);
+
+/* ---- node renumbering for meshes without locality in their ids (gmsh order; the reference keeps
+ * gmsh's tags as node ids, src/mesher.rs:663-671), host only — SURVEY §8(e) ----------------------
+ * Reverse Cuthill-McKee on the node graph of the elements.  new_of_old[i] = new id of node i; nodes
+ * no element references go last.  The caller permutes the node arrays and the connectivity (element
+ * order and local node order unchanged), calls mag_solve, and reads result j of node i at
+ * new_of_old[i]: the drop-in boundary keeps the original ids.  band_* (optional) = max |a-b| over
+ * the node pairs of every element, before and after.  Deterministic. */
+int mag_reorder_rcm(uint64_t n_nodes, uint64_t n_elems, const uint32_t *n0, const uint32_t *n1,
+                    const uint32_t *n2, uint32_t *new_of_old /* n_nodes */, uint64_t *band_before,
+                    uint64_t *band_after);
+int mag_mesh_band(uint64_t n_nodes, uint64_t n_elems, const uint32_t *n0, const uint32_t *n1,
+                  const uint32_t *n2, uint64_t *band);
 
 /* ---- synthetic meshes generated on the device ------------- */
 /* Plate(nx,ny,h): node (i,j) -> id j*(nx+1)+i at (i*h, j*h); cell -> [a,b,d],[a,d,c];

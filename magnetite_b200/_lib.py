@@ -100,7 +100,9 @@ _SIGNATURES = {
     "mag_system_spmv_bench": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
     "mag_csv_output": (C.c_int, [C.c_char_p, C.c_char_p, C.c_uint64, _vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp, _vp, _vp]),
     "mag_format_f64": (C.c_size_t, [C.c_double, C.c_char_p]),
-    "mag_csv_last_error": (C.c_char_p, []),
+    "mag_host_last_error": (C.c_char_p, []),
+    "mag_reorder_rcm": (C.c_int, [C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "mag_mesh_band": (C.c_int, [C.c_uint64, C.c_uint64, _vp, _vp, _vp, C.POINTER(C.c_uint64)]),
     "mag_devmesh_plate": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.POINTER(_vp)]),
     "mag_devmesh_perforated": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_double, C.c_uint32, C.c_uint32, C.c_double,
                                          C.POINTER(_vp)]),

@@ -65,9 +65,13 @@ struct Chunked {
     bool room() { return buf.size() < (1u << 20) || flush(); }
 };
 
-thread_local std::string g_csv_error;
-
 }  // namespace
+
+// message of the last failed host-only entry point on this thread (csv.cpp, reorder.cpp)
+namespace maghost {
+thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+}  // namespace maghost
 
 extern "C" size_t mag_format_f64(double v, char *out /* >= 400 bytes */) {
     const size_t n = format_f64(v, out);
@@ -75,21 +79,21 @@ extern "C" size_t mag_format_f64(double v, char *out /* >= 400 bytes */) {
     return n;
 }
 
-extern "C" const char *mag_csv_last_error(void) { return g_csv_error.c_str(); }
+extern "C" const char *mag_host_last_error(void) { return maghost::g_error.c_str(); }
 
 extern "C" int mag_csv_output(const char *nodes_path, const char *elements_path, uint64_t n_nodes, const double *x,
                               const double *y, const double *ux, const double *uy, uint64_t n_elems,
                               const uint32_t *n0, const uint32_t *n1, const uint32_t *n2, const double *stress) {
     if (!nodes_path || !elements_path || (n_nodes && (!x || !y || !ux || !uy)) ||
         (n_elems && (!n0 || !n1 || !n2 || !stress))) {
-        g_csv_error = "null argument";
+        maghost::set_error("null argument");
         return MAG_ERR_BAD_ARG;
     }
     std::FILE *nf = std::fopen(nodes_path, "wb");                 // post_processor.rs:24-31
-    if (!nf) { g_csv_error = std::string("Failed to create nodes.csv: ") + std::strerror(errno); return MAG_ERR_BAD_ARG; }
+    if (!nf) { maghost::set_error(std::string("Failed to create nodes.csv: ") + std::strerror(errno)); return MAG_ERR_BAD_ARG; }
     std::FILE *ef = std::fopen(elements_path, "wb");              // post_processor.rs:32-39
     if (!ef) {
-        g_csv_error = std::string("Failed to create elements.csv: ") + std::strerror(errno);
+        maghost::set_error(std::string("Failed to create elements.csv: ") + std::strerror(errno));
         std::fclose(nf);
         return MAG_ERR_BAD_ARG;
     }
@@ -126,6 +130,6 @@ extern "C" int mag_csv_output(const char *nodes_path, const char *elements_path,
     }
     ok = (std::fclose(nf) == 0) && ok;
     ok = (std::fclose(ef) == 0) && ok;
-    if (!ok) { g_csv_error = "short write"; return MAG_ERR_BAD_ARG; }
+    if (!ok) { maghost::set_error("short write"); return MAG_ERR_BAD_ARG; }
     return MAG_OK;
 }

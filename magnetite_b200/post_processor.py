@@ -40,7 +40,7 @@ def write_csv_fast(x, y, ux, uy, n0, n1, n2, stress, nodes_output: str, elements
                             _lib.ptr(ux), _lib.ptr(uy), n0.shape[0], _lib.ptr(n0), _lib.ptr(n1), _lib.ptr(n2),
                             _lib.ptr(stress))
     if rc != 0:
-        raise MagnetiteError.Solver((lib.mag_csv_last_error() or b"").decode(), code=rc)
+        raise MagnetiteError.Solver((lib.mag_host_last_error() or b"").decode(), code=rc)
 
 
 def write_csv_arrays(x, y, ux, uy, n0, n1, n2, stress, nodes_output: str, elements_output: str) -> None:

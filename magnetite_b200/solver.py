@@ -162,8 +162,24 @@ class System:
 
 
 def solve_soa(mesh: MeshSoA, meta: ModelMetadata, ctx: Optional[_lib.Context] = None,
-              options: Optional[MagOptions] = None, want_sigma: bool = False) -> Solution:
-    """One call through mag_solve with host buffers (the end-to-end path the Rust shim takes)."""
+              options: Optional[MagOptions] = None, want_sigma: bool = False, reorder: bool = False) -> Solution:
+    """One call through mag_solve with host buffers (the end-to-end path the Rust shim takes).
+
+    `reorder=True` renumbers the nodes with reverse Cuthill-McKee first when that narrows the band
+    (meshes in gmsh order) and returns the results in the ORIGINAL numbering; see
+    reorder.py for what that does and does not change."""
+    if reorder:
+        from . import reorder as R
+        new_of_old, before, after = R.rcm(mesh)
+        info = {"applied": after < before, "band_before": before, "band_after": after}
+        if not info["applied"]:
+            sol = solve_soa(mesh, meta, ctx, options, want_sigma)
+        else:
+            sol = solve_soa(R.permute_mesh(mesh, new_of_old), meta, ctx, options, want_sigma)
+            for k in ("ux", "uy", "fx", "fy"):
+                setattr(sol, k, R.unpermute_nodal(getattr(sol, k), new_of_old))
+        sol.stats["reorder"] = info
+        return sol
     ctx = ctx or default_context()
     m = mesh.normalised()
     n, e = m.n_nodes, m.n_elems
@@ -267,11 +283,12 @@ def compute_element_area(element: Element, nodes: Sequence[Node]) -> float:
 
 
 def run(nodes: List[Node], elements: List[Element], model_metadata: ModelMetadata,
-        options: Optional[MagOptions] = None, quiet: bool = False) -> None:
+        options: Optional[MagOptions] = None, quiet: bool = False, reorder: bool = False) -> None:
     """solver::run (solver.rs:543-586): fills node.ux/uy/fx/fy and element.stress in place.
 
     Default options reproduce the reference's solver semantics (plain CG from x0 = 0, absolute
-    cost 1e-4, 1e7 iterations: `compat=1`).  Pass options for the north-star Jacobi-PCG.
+    cost 1e-4, 1e7 iterations: `compat=1`).  Pass options for the north-star Jacobi-PCG, and
+    `reorder=True` for meshes in gmsh order (results stay in the caller's numbering).
     """
     say = (lambda *_: None) if quiet else print
     mesh = MeshSoA.from_aos(nodes, elements)
@@ -280,7 +297,7 @@ def run(nodes: List[Node], elements: List[Element], model_metadata: ModelMetadat
     say("info: building total stiffness matrix...")               # solver.rs:570
     say("info: setting up system...")                             # solver.rs:416
     say("info: solving...")                                       # solver.rs:437
-    sol = solve_soa(mesh, model_metadata, options=opt)
+    sol = solve_soa(mesh, model_metadata, options=opt, reorder=reorder)
     st = sol.stats
     say(f"info: finished conjugate gradient approximation in {st['iters']} iterations")  # :101-104
     say("info: solved system in {:.3f} seconds".format(st["ms_solve"] / 1e3))            # :441

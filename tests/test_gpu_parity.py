@@ -561,3 +561,40 @@ def test_cpp_cli_full_flow_matches_python_flow(ctx, tmp_path):
     assert (tmp_path / "nodes.csv").read_bytes() == (tmp_path / "n_py.csv").read_bytes()
     assert (tmp_path / "elements.csv").read_bytes() == (tmp_path / "e_py.csv").read_bytes()
     assert max(n.ux for n in nodes) == 3.0 and min(n.ux for n in nodes) == 0.0
+
+
+def test_rcm_reordered_solve_keeps_the_callers_numbering(ctx):
+    """a mesh whose node ids carry no locality (gmsh order) is renumbered on the host
+    (mag_reorder_rcm) before the solve and the results come back in the caller's numbering.  The
+    shuffled plate has a band of ~36 k reduced DOFs (32-bit SELL columns); after RCM it is banded
+    again (16-bit offsets).  Same answers within the north-star tolerances, and equal to the solve of
+    the plate in its natural numbering."""
+    from magnetite_b200 import reorder
+    base = meshgen.jitter(meshgen.plate(180, 100))
+    perm = np.random.default_rng(21).permutation(base.n_nodes).astype(np.uint32)
+    mesh = reorder.permute_mesh(base, perm)
+    opt = _lib.default_options(rel_tol=1e-12)
+    plain = solver.solve_soa(mesh, META, ctx, opt)
+    ro = solver.solve_soa(mesh, META, ctx, opt, reorder=True)
+    info = ro.stats["reorder"]
+    assert info["applied"] and info["band_before"] > base.n_nodes // 2 and info["band_after"] <= 110
+    assert plain.stats["sell_index_bits"] == 32 and ro.stats["sell_index_bits"] == 16
+    assert ro.stats["nnz"] == plain.stats["nnz"] and ro.stats["n_free"] == plain.stats["n_free"]
+    u_plain, u_ro = np.concatenate([plain.ux, plain.uy]), np.concatenate([ro.ux, ro.uy])
+    assert rel_l2(u_ro, u_plain) < 1e-9
+    assert np.abs(ro.stress - plain.stress).max() / np.abs(plain.stress).max() < 1e-8
+    f_plain, f_ro = np.concatenate([plain.fx, plain.fy]), np.concatenate([ro.fx, ro.fy])
+    assert np.abs(f_ro - f_plain).max() / np.abs(f_plain).max() < 1e-7
+    nat = solver.solve_soa(base, META, ctx, opt)                       # the plate as generated
+    # base node i is node perm[i] of the shuffled mesh
+    assert rel_l2(np.concatenate([ro.ux[perm], ro.uy[perm]]), np.concatenate([nat.ux, nat.uy])) < 1e-9
+    # a structured plate already numbered along its short side is left alone
+    tall = solver.solve_soa(meshgen.plate(12, 40), META, ctx, opt, reorder=True)
+    assert not tall.stats["reorder"]["applied"]
+    # the drop-in entry point takes the same switch and fills the caller's lists in their order
+    nodes, elements = reorder.permute_mesh(meshgen.plate(14, 9), np.random.default_rng(2).permutation(150).astype(np.uint32)).to_aos()
+    nodes2, elements2 = [Node(Vertex(n.vertex.x, n.vertex.y), n.ux, n.uy, n.fx, n.fy) for n in nodes], [Element(list(e.nodes)) for e in elements]
+    solver.run(nodes, elements, META, options=opt, quiet=True)
+    solver.run(nodes2, elements2, META, options=opt, quiet=True, reorder=True)
+    assert rel_l2(np.array([n.ux for n in nodes2] + [n.uy for n in nodes2]), np.array([n.ux for n in nodes] + [n.uy for n in nodes])) < 1e-9
+    assert np.abs(np.array([e.stress for e in elements2]) - np.array([e.stress for e in elements])).max() < 1e-8 * max(abs(e.stress) for e in elements)
