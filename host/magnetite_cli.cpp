@@ -2,14 +2,20 @@
 //
 //   magnetite_b200 input.json geom.msh [--skip]        mesh from gmsh (or geometry.write_msh) + input.json
 //                                                      -> nodes.csv, elements.csv in the working directory
+//   magnetite_b200 input.json geom.msh --reorder       the same with the nodes renumbered (reverse Cuthill-McKee)
+//                                                      around the solve; the CSVs keep the mesh file's numbering
 //   magnetite_b200 --dump-rules input.json             print the parsed metadata and boundary rules (no GPU)
+//   magnetite_b200 --band geom.msh                     node band of the mesh as numbered and after RCM (no GPU)
 //
 // The reference shells out to gmsh for the .msh (mesher.rs:501-506); that step is out of scope, so the
 // CLI starts from the mesh file.  `--skip` is accepted for compatibility (the plot step never runs here).
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
+#include "../include/magnetite_b200.h"
 #include "magnetite_io.hpp"
 
 using namespace magnetite;
@@ -34,10 +40,28 @@ int main(int argc, char **argv) {
                             opt(r.target.ux).c_str(), opt(r.target.uy).c_str(), opt(r.target.fx).c_str(), opt(r.target.fy).c_str());
             return 0;
         }
+        if (argc == 3 && !std::strcmp(argv[1], "--band")) {
+            std::vector<Node> nodes;
+            std::vector<Element> elements;
+            mesher::parse_mesh(argv[2], nodes, elements);
+            std::vector<std::uint32_t> c[3], new_of_old(nodes.size());
+            for (const Element &e : elements)
+                for (int k = 0; k < 3; ++k) c[k].push_back((std::uint32_t)e.nodes[k]);
+            std::uint64_t before = 0, after = 0;
+            const int rc = mag_reorder_rcm(nodes.size(), elements.size(), c[0].data(), c[1].data(), c[2].data(),
+                                           new_of_old.data(), &before, &after);
+            if (rc != MAG_OK) throw MagnetiteError(MagnetiteError::Kind::Solver, mag_host_last_error(), rc);
+            std::printf("nodes %zu elements %zu band %llu rcm %llu\n", nodes.size(), elements.size(),
+                        (unsigned long long)before, (unsigned long long)after);
+            return 0;
+        }
         if (argc < 3) {
-            std::fprintf(stderr, "usage: magnetite_b200 input.json geom.msh [--skip]\n");
+            std::fprintf(stderr, "usage: magnetite_b200 input.json geom.msh [--skip] [--reorder]\n");
             return 2;
         }
+        SolverOptions so;
+        for (int i = 3; i < argc; ++i)
+            if (!std::strcmp(argv[i], "--reorder")) so.reorder = true;
         const std::string input_file = argv[1], mesh_file = argv[2];
         if (mesh_file.size() < 4 || mesh_file.substr(mesh_file.size() - 4) != ".msh")
             throw MagnetiteError(MagnetiteError::Kind::Input,
@@ -50,7 +74,7 @@ int main(int argc, char **argv) {
         mesher::check_ccw(elements, solver::element_areas(elements, nodes));     // mesher.rs:691-693
         std::printf("info: loaded %zu nodes and %zu elements\n", nodes.size(), elements.size());
         mesher::apply_boundary_conditions(j, nodes, false);                      // mesher.rs:971
-        solver::run(nodes, elements, md);                                        // main.rs:64
+        solver::run(nodes, elements, md, so);                                    // main.rs:64
         post_processor::csv_output(elements, nodes, "nodes.csv", "elements.csv");   // main.rs:67-69
     } catch (const MagnetiteError &err) {
         std::fprintf(stderr, "Received error: %s\n", err.what());                // main.rs:46

@@ -1,11 +1,13 @@
 // magnetite_host.cpp — see magnetite_host.hpp.  Host-only C++17; links libmagnetite_b200.so.
 #include "magnetite_host.hpp"
 
+#include <cerrno>
 #include <charconv>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 
 #include "../include/magnetite_b200.h"
@@ -77,6 +79,21 @@ Flat flatten(const std::vector<Node> &nodes, const std::vector<Element> &element
     return f;
 }
 
+// The same mesh with node i renamed new_of_old[i] (element order and orientation untouched).
+Flat permuted(const Flat &f, const std::vector<std::uint32_t> &new_of_old) {
+    Flat g = f;
+    for (std::size_t i = 0; i < f.x.size(); ++i) {
+        const std::uint32_t j = new_of_old[i];
+        g.x[j] = f.x[i]; g.y[j] = f.y[i];
+        g.ux[j] = f.ux[i]; g.uy[j] = f.uy[i]; g.fx[j] = f.fx[i]; g.fy[j] = f.fy[i];
+        g.known[j] = f.known[i];
+    }
+    for (std::size_t e = 0; e < f.n0.size(); ++e) {
+        g.n0[e] = new_of_old[f.n0[e]]; g.n1[e] = new_of_old[f.n1[e]]; g.n2[e] = new_of_old[f.n2[e]];
+    }
+    return g;
+}
+
 }  // namespace
 
 namespace solver {
@@ -86,7 +103,20 @@ void run(std::vector<Node> &nodes, std::vector<Element> &elements, const ModelMe
     auto say = [&](const char *s) { if (!so.quiet) std::printf("%s\n", s); };
     say("info: building element stiffness matrices...");           // solver.rs:551
     say("info: building total stiffness matrix...");               // solver.rs:570
-    const Flat f = flatten(nodes, elements);
+    Flat f = flatten(nodes, elements);
+    std::vector<std::uint32_t> new_of_old;                         // empty: solved in the caller's numbering
+    if (so.reorder) {                                              // gmsh order has no band
+        new_of_old.resize(nodes.size());
+        std::uint64_t before = 0, after = 0;
+        const int rc = mag_reorder_rcm(f.x.size(), f.n0.size(), f.n0.data(), f.n1.data(), f.n2.data(),
+                                       new_of_old.data(), &before, &after);
+        if (rc != MAG_OK) throw MagnetiteError(MagnetiteError::Kind::Solver, mag_host_last_error(), rc);
+        if (after < before) f = permuted(f, new_of_old);
+        else new_of_old.clear();
+        if (!so.quiet)
+            std::printf("info: node band %llu -> %llu (%s)\n", (unsigned long long)before, (unsigned long long)after,
+                        new_of_old.empty() ? "kept the mesher's numbering" : "renumbered for the solve");
+    }
     const mag_mesh mesh = f.view();
     const mag_material mat{md.youngs_modulus, md.poisson_ratio, md.part_thickness};
     mag_options opt;
@@ -112,8 +142,9 @@ void run(std::vector<Node> &nodes, std::vector<Element> &elements, const ModelMe
         std::printf("info: solved system in %.3f seconds\n", st.ms_solve / 1e3);   // solver.rs:441
     }
     for (std::size_t i = 0; i < n; ++i) {                          // solver.rs:476-482
-        nodes[i].ux = ux[i]; nodes[i].uy = uy[i];
-        nodes[i].fx = fx[i]; nodes[i].fy = fy[i];
+        const std::size_t j = new_of_old.empty() ? i : new_of_old[i];
+        nodes[i].ux = ux[j]; nodes[i].uy = uy[j];
+        nodes[i].fx = fx[j]; nodes[i].fy = fy[j];
     }
     for (std::size_t i = 0; i < e; ++i) elements[i].stress = stress[i];   // solver.rs:532-533
     say("info: solve complete");                                   // solver.rs:484
@@ -160,12 +191,15 @@ std::string format_f64(double v) {
     return out;
 }
 
+// Rust's Display of std::io::Error, which the reference embeds in its message (post_processor.rs:27-29)
+static std::string os_error(int err) { return std::string(std::strerror(err)) + " (os error " + std::to_string(err) + ")"; }
+
 void csv_output(const std::vector<Element> &elements, const std::vector<Node> &nodes,
                 const std::string &nodes_output, const std::string &elements_output, bool quiet) {
     std::ofstream nf(nodes_output, std::ios::binary | std::ios::trunc);
-    if (!nf) throw MagnetiteError(MagnetiteError::Kind::Solver, "Failed to create nodes.csv: " + nodes_output);
+    if (!nf) throw MagnetiteError(MagnetiteError::Kind::Solver, "Failed to create nodes.csv: " + os_error(errno));
     std::ofstream ef(elements_output, std::ios::binary | std::ios::trunc);
-    if (!ef) throw MagnetiteError(MagnetiteError::Kind::Solver, "Failed to create elements.csv: " + elements_output);
+    if (!ef) throw MagnetiteError(MagnetiteError::Kind::Solver, "Failed to create elements.csv: " + os_error(errno));
     nf << "x,y,ux,uy\n";                                           // post_processor.rs:42
     for (const Node &nd : nodes) {
         if (!nd.ux || !nd.uy)                                      // the reference unwrap()s (:50-51)

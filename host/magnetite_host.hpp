@@ -47,6 +47,8 @@ struct SolverOptions {         // the reference has constants only (solver.rs:18
     double rel_tol = 1e-9;
     bool quiet = false;
     int device = 0;
+    bool reorder = false;      // renumber the nodes (reverse Cuthill-McKee, mag_reorder_rcm) around the solve when that
+                               // narrows the band — meshes in gmsh order; results stay in the caller's numbering
 };
 
 namespace solver {

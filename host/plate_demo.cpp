@@ -23,6 +23,15 @@ static int format_selftest() {
     }
     MagnetiteError e(MagnetiteError::Kind::PostProcessor, "x");
     if (std::string(e.what()) != "Post Processor error: x") ++bad;
+    try {                                        // post_processor.rs:24-31 with Rust's io::Error Display
+        post_processor::csv_output({}, {}, "/nonexistent-dir/nodes.csv", "/nonexistent-dir/elements.csv", true);
+        ++bad;
+    } catch (const MagnetiteError &err) {
+        if (std::string(err.what()) != "Solver error: Failed to create nodes.csv: No such file or directory (os error 2)") {
+            std::printf("MISMATCH %s\n", err.what());
+            ++bad;
+        }
+    }
     std::printf(bad ? "FORMAT_FAIL\n" : "FORMAT_OK\n");
     return bad;
 }

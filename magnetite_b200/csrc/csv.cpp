@@ -4,6 +4,7 @@
 // whole GPU solve, so the writer formats into 1 MiB chunks.  No CUDA here.
 #include <charconv>
 #include <cmath>
+#include <cerrno>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -53,6 +54,9 @@ size_t format_f64(double v, char *out) {
     return (size_t)(p - out);
 }
 
+// Rust's Display of std::io::Error, which the reference embeds in its message (post_processor.rs:27-29)
+std::string os_error(int err) { return std::string(std::strerror(err)) + " (os error " + std::to_string(err) + ")"; }
+
 struct Chunked {
     std::FILE *f;
     std::string buf;
@@ -90,10 +94,10 @@ extern "C" int mag_csv_output(const char *nodes_path, const char *elements_path,
         return MAG_ERR_BAD_ARG;
     }
     std::FILE *nf = std::fopen(nodes_path, "wb");                 // post_processor.rs:24-31
-    if (!nf) { maghost::set_error(std::string("Failed to create nodes.csv: ") + std::strerror(errno)); return MAG_ERR_BAD_ARG; }
+    if (!nf) { maghost::set_error("Failed to create nodes.csv: " + os_error(errno)); return MAG_ERR_BAD_ARG; }
     std::FILE *ef = std::fopen(elements_path, "wb");              // post_processor.rs:32-39
     if (!ef) {
-        maghost::set_error(std::string("Failed to create elements.csv: ") + std::strerror(errno));
+        maghost::set_error("Failed to create elements.csv: " + os_error(errno));
         std::fclose(nf);
         return MAG_ERR_BAD_ARG;
     }

@@ -43,17 +43,22 @@ def write_csv_fast(x, y, ux, uy, n0, n1, n2, stress, nodes_output: str, elements
         raise MagnetiteError.Solver((lib.mag_host_last_error() or b"").decode(), code=rc)
 
 
+def _os_error(err: OSError) -> str:
+    """Rust's Display of std::io::Error, which the reference embeds in its message (post_processor.rs:27-29)."""
+    return f"{err.strerror} (os error {err.errno})"
+
+
 def write_csv_arrays(x, y, ux, uy, n0, n1, n2, stress, nodes_output: str, elements_output: str) -> None:
     """Array-level writer in pure Python (buffered; the reference issues one unbuffered write per row)."""
     try:
         nf = open(nodes_output, "w", newline="")
     except OSError as err:                                   # post_processor.rs:24-31
-        raise MagnetiteError.Solver(f"Failed to create nodes.csv: {err}")
+        raise MagnetiteError.Solver(f"Failed to create nodes.csv: {_os_error(err)}")
     try:
         ef = open(elements_output, "w", newline="")
     except OSError as err:                                   # post_processor.rs:32-39
         nf.close()
-        raise MagnetiteError.Solver(f"Failed to create elements.csv: {err}")
+        raise MagnetiteError.Solver(f"Failed to create elements.csv: {_os_error(err)}")
     f = rust_f64_display
     with nf, ef:
         nf.write("x,y,ux,uy\n")                              # post_processor.rs:42

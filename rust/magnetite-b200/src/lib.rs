@@ -84,6 +84,13 @@ pub mod sys {
         pub fn mag_solve(ctx: *mut mag_ctx, mesh: *const mag_mesh, mat: *const mag_material,
                          opt: *const mag_options, out: *mut mag_result, stats: *mut mag_stats) -> c_int;
         pub fn mag_element_area(ctx: *mut mag_ctx, mesh: *const mag_mesh, area: *mut f64) -> c_int;
+        // host-only entry points (no CUDA device needed); errors through mag_host_last_error
+        pub fn mag_host_last_error() -> *const c_char;
+        pub fn mag_reorder_rcm(n_nodes: u64, n_elems: u64, n0: *const u32, n1: *const u32, n2: *const u32,
+                               new_of_old: *mut u32, band_before: *mut u64, band_after: *mut u64) -> c_int;
+        pub fn mag_csv_output(nodes_path: *const c_char, elements_path: *const c_char, n_nodes: u64,
+                              x: *const f64, y: *const f64, ux: *const f64, uy: *const f64, n_elems: u64,
+                              n0: *const u32, n1: *const u32, n2: *const u32, stress: *const f64) -> c_int;
     }
 }
 
@@ -100,6 +107,10 @@ pub const TARGET_CG_COST: f64 = 1e-4;           // solver.rs:19
 
 fn last_error() -> String {
     unsafe { CStr::from_ptr(sys::mag_last_error()).to_string_lossy().into_owned() }
+}
+
+fn host_last_error() -> String {
+    unsafe { CStr::from_ptr(sys::mag_host_last_error()).to_string_lossy().into_owned() }
 }
 
 struct Flat {
@@ -129,14 +140,54 @@ fn flatten(nodes: &Vec<Node>, elements: &Vec<Element>) -> Flat {
     f
 }
 
-/// Drop-in for `solver::run` (src/solver.rs:543-586).
+/// The same mesh with node i renamed `new_of_old[i]`; element order and orientation untouched.
+fn permuted(f: &Flat, new_of_old: &[u32]) -> Flat {
+    let n = f.x.len();
+    let mut g = Flat { x: vec![0.0; n], y: vec![0.0; n], ux: vec![0.0; n], uy: vec![0.0; n], fx: vec![0.0; n],
+                       fy: vec![0.0; n], known: vec![0u8; n], n0: Vec::with_capacity(f.n0.len()),
+                       n1: Vec::with_capacity(f.n0.len()), n2: Vec::with_capacity(f.n0.len()) };
+    for i in 0..n {
+        let j = new_of_old[i] as usize;
+        g.x[j] = f.x[i]; g.y[j] = f.y[i];
+        g.ux[j] = f.ux[i]; g.uy[j] = f.uy[i]; g.fx[j] = f.fx[i]; g.fy[j] = f.fy[i];
+        g.known[j] = f.known[i];
+    }
+    for e in 0..f.n0.len() {
+        g.n0.push(new_of_old[f.n0[e] as usize]);
+        g.n1.push(new_of_old[f.n1[e] as usize]);
+        g.n2.push(new_of_old[f.n2[e] as usize]);
+    }
+    g
+}
+
+/// Drop-in for `solver::run` (src/solver.rs:543-586).  `MAGNETITE_B200_REORDER=1` in the environment
+/// renumbers the nodes (reverse Cuthill-McKee) around the solve — for meshes in gmsh order; the
+/// caller's vectors keep their order.
 pub fn run(nodes: &mut Vec<Node>, elements: &mut Vec<Element>, model_metadata: &ModelMetadata)
     -> Result<(), MagnetiteError>
 {
+    let reorder = std::env::var("MAGNETITE_B200_REORDER").map(|v| v == "1").unwrap_or(false);
+    run_with(nodes, elements, model_metadata, reorder)
+}
+
+pub fn run_with(nodes: &mut Vec<Node>, elements: &mut Vec<Element>, model_metadata: &ModelMetadata,
+                reorder: bool) -> Result<(), MagnetiteError>
+{
     println!("info: building element stiffness matrices...");
     println!("info: building total stiffness matrix...");
-    let f = flatten(nodes, elements);
+    let mut f = flatten(nodes, elements);
     let (n, e) = (nodes.len(), elements.len());
+    let mut new_of_old: Vec<u32> = Vec::new();           // empty: solved in the caller's numbering
+    if reorder {
+        new_of_old = vec![0u32; n];
+        let (mut before, mut after) = (0u64, 0u64);
+        let rc = unsafe {
+            sys::mag_reorder_rcm(n as u64, e as u64, f.n0.as_ptr(), f.n1.as_ptr(), f.n2.as_ptr(),
+                                 new_of_old.as_mut_ptr(), &mut before, &mut after)
+        };
+        if rc != 0 { return Err(MagnetiteError::Solver(host_last_error())); }
+        if after < before { f = permuted(&f, &new_of_old); } else { new_of_old.clear(); }
+    }
     let mesh = sys::mag_mesh {
         n_nodes: n as u64, n_elems: e as u64, x: f.x.as_ptr(), y: f.y.as_ptr(),
         n0: f.n0.as_ptr(), n1: f.n1.as_ptr(), n2: f.n2.as_ptr(),
@@ -170,12 +221,40 @@ pub fn run(nodes: &mut Vec<Node>, elements: &mut Vec<Element>, model_metadata: &
     println!("info: finished conjugate gradient approximation in {} iterations", stats.iters);
     println!("info: solved system in {:.3} seconds", stats.ms_solve / 1e3);
     for (i, node) in nodes.iter_mut().enumerate() {          // solver.rs:476-482
-        node.ux = Some(ux[i]); node.uy = Some(uy[i]);
-        node.fx = Some(fx[i]); node.fy = Some(fy[i]);
+        let j = if new_of_old.is_empty() { i } else { new_of_old[i] as usize };
+        node.ux = Some(ux[j]); node.uy = Some(uy[j]);
+        node.fx = Some(fx[j]); node.fy = Some(fy[j]);
     }
     for (i, el) in elements.iter_mut().enumerate() {          // solver.rs:532-533
         el.stress = Some(stress[i]);
     }
     println!("info: solve complete");
+    Ok(())
+}
+
+/// Drop-in for `post_processor::csv_output` (src/post_processor.rs:18-83): same files byte for byte
+/// (Rust `{}` float formatting is reproduced in the library), written through 1 MiB buffers instead of
+/// one unbuffered write per row.
+pub fn csv_output(elements: &Vec<Element>, nodes: &Vec<Node>, nodes_output: &str, elements_output: &str)
+    -> Result<(), MagnetiteError>
+{
+    use std::ffi::CString;
+    let x: Vec<f64> = nodes.iter().map(|n| n.vertex.x).collect();
+    let y: Vec<f64> = nodes.iter().map(|n| n.vertex.y).collect();
+    let ux: Vec<f64> = nodes.iter().map(|n| n.ux.unwrap()).collect();       // the reference unwraps too (:50-51)
+    let uy: Vec<f64> = nodes.iter().map(|n| n.uy.unwrap()).collect();
+    let n0: Vec<u32> = elements.iter().map(|e| e.nodes[0] as u32).collect();
+    let n1: Vec<u32> = elements.iter().map(|e| e.nodes[1] as u32).collect();
+    let n2: Vec<u32> = elements.iter().map(|e| e.nodes[2] as u32).collect();
+    let stress: Vec<f64> = elements.iter().map(|e| e.stress.unwrap()).collect();   // :70
+    let bad_path = |_| MagnetiteError::Solver("output path contains a NUL byte".to_string());
+    let np = CString::new(nodes_output).map_err(bad_path)?;
+    let ep = CString::new(elements_output).map_err(bad_path)?;
+    let rc = unsafe {
+        sys::mag_csv_output(np.as_ptr(), ep.as_ptr(), x.len() as u64, x.as_ptr(), y.as_ptr(), ux.as_ptr(),
+                            uy.as_ptr(), n0.len() as u64, n0.as_ptr(), n1.as_ptr(), n2.as_ptr(), stress.as_ptr())
+    };
+    if rc != 0 { return Err(MagnetiteError::Solver(host_last_error())); }
+    println!("info: wrote output to {} and {}", nodes_output, elements_output);   // :77-80
     Ok(())
 }

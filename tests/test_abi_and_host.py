@@ -219,5 +219,10 @@ def test_library_csv_writer_matches_python_writer(tmp_path, built):
     for v in list(rng.normal(size=300) * 10.0 ** rng.integers(-300, 300, 300)) + [5e-324, 1.7976931348623157e308, -0.0]:
         lib.mag_format_f64(float(v), buf)
         assert buf.value.decode() == post_processor.rust_f64_display(v)
-    with pytest.raises(MagnetiteError, match="Failed to create nodes.csv"):
-        post_processor.write_csv_fast(x, y, ux, uy, n0, n1, n2, stress, str(tmp_path / "no" / "n.csv"), str(tmp_path / "e.csv"))
+    # post_processor.rs:24-39: the io::Error's Display inside MagnetiteError::Solver, from both writers
+    want = r"^Solver error: Failed to create nodes.csv: No such file or directory \(os error 2\)$"
+    for writer in (post_processor.write_csv_fast, post_processor.write_csv_arrays):
+        with pytest.raises(MagnetiteError, match=want):
+            writer(x, y, ux, uy, n0, n1, n2, stress, str(tmp_path / "no" / "n.csv"), str(tmp_path / "e.csv"))
+        with pytest.raises(MagnetiteError, match=want.replace("nodes", "elements")):
+            writer(x, y, ux, uy, n0, n1, n2, stress, str(tmp_path / "n.csv"), str(tmp_path / "no" / "e.csv"))

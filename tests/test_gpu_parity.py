@@ -561,6 +561,17 @@ def test_cpp_cli_full_flow_matches_python_flow(ctx, tmp_path):
     assert (tmp_path / "nodes.csv").read_bytes() == (tmp_path / "n_py.csv").read_bytes()
     assert (tmp_path / "elements.csv").read_bytes() == (tmp_path / "e_py.csv").read_bytes()
     assert max(n.ux for n in nodes) == 3.0 and min(n.ux for n in nodes) == 0.0
+    # --reorder: renumbered around the solve, CSVs in the mesh file's numbering, same values to rounding
+    (tmp_path / "ro").mkdir()
+    r = subprocess.run([str(root / "host" / "magnetite_b200"), inp, str(tmp_path / "geom.msh"), "--skip", "--reorder"],
+                       cwd=tmp_path / "ro", capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "info: node band " in r.stdout, r.stdout + r.stderr
+    a = np.loadtxt(tmp_path / "nodes.csv", delimiter=",", skiprows=1)
+    b = np.loadtxt(tmp_path / "ro" / "nodes.csv", delimiter=",", skiprows=1)
+    assert np.array_equal(a[:, :2], b[:, :2]) and rel_l2(b[:, 2:], a[:, 2:]) < 1e-9
+    ea = np.loadtxt(tmp_path / "elements.csv", delimiter=",", skiprows=1)
+    eb = np.loadtxt(tmp_path / "ro" / "elements.csv", delimiter=",", skiprows=1)
+    assert np.array_equal(ea[:, :3], eb[:, :3]) and np.abs(eb[:, 3] - ea[:, 3]).max() < 1e-8 * np.abs(ea[:, 3]).max()
 
 
 def test_rcm_reordered_solve_keeps_the_callers_numbering(ctx):

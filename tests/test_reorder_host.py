@@ -142,3 +142,22 @@ def test_rcm_edge_cases(built):
         reorder.rcm(mesh)
     with pytest.raises(MagnetiteError, match="references a node"):
         reorder.mesh_band(mesh)
+
+
+def test_cpp_cli_band_mode_agrees_with_the_python_binding(built, tmp_path):
+    """`magnetite_b200 --band geom.msh` (C++ host layer -> mag_reorder_rcm, no GPU) reports the same band as the
+    Python binding for the same mesh file."""
+    import subprocess
+    from magnetite_b200 import geometry
+    root = Path(__file__).resolve().parent.parent
+    subprocess.run(["make", "-C", str(root / "host")], check=True, capture_output=True)
+    _, mesh, _ = _example("example_cover")
+    conn = np.stack([mesh.n0, mesh.n1, mesh.n2], 1).astype(int)
+    geometry.write_msh(str(tmp_path / "geom.msh"), mesh.x, mesh.y, conn)
+    r = subprocess.run([str(root / "host" / "magnetite_b200"), "--band", str(tmp_path / "geom.msh")],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    nodes, elements = geometry.parse_mesh(str(tmp_path / "geom.msh"))            # the numbering the CLI saw
+    _, before, after = reorder.rcm(MeshSoA.from_aos(nodes, elements))
+    assert r.stdout.split() == ["nodes", str(len(nodes)), "elements", str(len(elements)), "band", str(before), "rcm", str(after)]
+    assert after * 20 < before
