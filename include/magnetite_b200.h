@@ -89,7 +89,8 @@ typedef struct {
     int32_t want_sigma;      /* also return sx,sy,txy per element                      */
     int32_t allreduce;       /* multi-GPU dot products: 0 peer-memory mailbox (default), 1 NCCL  */
     int32_t coarse_aggregates; /* precond 2: number of aggregates (0 = auto, at most 2048)       */
-    int32_t reserved;
+    int32_t assembly;        /* 0 (default): COO keys, stable sort, segmented reduction; 1: gather — per-node
+                              * incidence lists, K_e rows recomputed (same K bit for bit; was `reserved`) */
     void *stream;            /* cudaStream_t to run on, or NULL for the ctx's own      */
 } mag_options;
 

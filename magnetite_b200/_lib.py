@@ -44,7 +44,7 @@ class MagOptions(C.Structure):
                 ("precond", C.c_int32), ("compat", C.c_int32), ("cost_kind", C.c_int32),
                 ("drop_exact_zeros", C.c_int32), ("check_every", C.c_int32),
                 ("spmv_format", C.c_int32), ("want_sigma", C.c_int32), ("allreduce", C.c_int32),
-                ("coarse_aggregates", C.c_int32), ("reserved", C.c_int32),
+                ("coarse_aggregates", C.c_int32), ("assembly", C.c_int32),
                 ("stream", C.c_void_p)]
 
 

@@ -18,6 +18,7 @@
 #include "comm.cuh"
 #include "common.cuh"
 #include "element.cuh"
+#include "gather.cuh"
 #include "pcg.cuh"
 #include "spmv.cuh"
 
@@ -186,58 +187,66 @@ static void assemble_impl(mag_ctx *ctx, const mag_mesh *m, const mag_material *m
     if ((uint64_t)El * 9 >= (1ull << 32))
         fail(MAG_ERR_BAD_ARG, "this rank would assemble %zu elements; 9 COO keys each must stay below 2^32: use more GPUs", El);
     const uint32_t *elist_p = (nranks > 1) ? elist.p : nullptr;
-    DevBuf<double> kblk(ctx, El * 36);
-    if (El)
-        MAG_LAUNCH(ctx, element_stiffness_kernel, cdiv(El, kElemThreads), kElemThreads, 0,
-                   (const double2 *)S->xy.p, (const uint32_t *)S->n0.p, (const uint32_t *)S->n1.p,
-                   (const uint32_t *)S->n2.p, elist_p, El, 1, kblk.p);
-    st.ms_elem = phase.stop();
-
-    // ---- COO keys + stable sort ----------------------------------------------
-    phase.start();
-    const size_t n_keys = El * 9;
-    const int bits = bits_for(N + 1);
-    DevBuf<uint64_t> keys(ctx, n_keys), keys_alt(ctx, n_keys);
-    DevBuf<uint32_t> pay(ctx, n_keys), pay_alt(ctx, n_keys);
-    if (El) {
-        MAG_LAUNCH(ctx, emit_keys_kernel, cdiv(El, 256), 256, 0, (const uint32_t *)S->n0.p,
-                   (const uint32_t *)S->n1.p, (const uint32_t *)S->n2.p, elist_p, El, bits, S->node_lo,
-                   S->node_hi, keys.p, pay.p);
-        radix_sort_pairs(ctx, keys.p, pay.p, keys_alt.p, pay_alt.p, n_keys, 2 * bits);
-    }
-    keys_alt.release();
-    pay_alt.release();
-    elist.release();
-    st.ms_sort = phase.stop();
-
-    // ---- segmented reduction into BSR ------------------------------------------
-    phase.start();
     BsrMatrix &K = S->K;
     K.node_lo = S->node_lo; K.node_hi = S->node_hi;
     const uint32_t n_own = K.node_hi - K.node_lo;
-    K.browptr.alloc(ctx, (size_t)n_own + 1);
-    K.browptr.zero();
-    {
-        DevBuf<uint32_t> head(ctx, n_keys + 1);
-        if (n_keys)
-            MAG_LAUNCH(ctx, mark_heads_kernel, cdiv(n_keys, 256), 256, 0, (const uint64_t *)keys.p,
-                       n_keys, bits, K.node_lo, head.p, K.browptr.p);
-        DevBuf<uint32_t> uid(ctx, n_keys + 1);      // exclusive scan of head; uid[n_keys] = #blocks
-        exclusive_scan_u32(ctx, head.p, n_keys, uid.p, n_keys + 1);
-        exclusive_scan_u32(ctx, K.browptr.p, n_own, K.browptr.p, (size_t)n_own + 1);
-        K.n_blocks = read_u32(ctx, uid.p + n_keys);
-        K.bcol.alloc(ctx, K.n_blocks);
-        K.bval.alloc(ctx, (size_t)K.n_blocks * 4);
-        if (n_keys)
-            MAG_LAUNCH(ctx, segment_reduce_kernel, cdiv(n_keys, 256), 256, 0, (const uint64_t *)keys.p,
-                       (const uint32_t *)pay.p, (const uint32_t *)head.p, (const uint32_t *)uid.p,
-                       n_keys, bits, (const double *)kblk.p, K.bcol.p, K.bval.p);
+    const bool use_gather = opt && opt->assembly == 1;
+    if (use_gather) {
+        // gather assembly (gather.cuh): no K_e in memory, 3E incidences sorted by node instead of 9E COO keys
+        st.ms_elem = phase.stop();                  // only the rank's element list: K_e rows are recomputed in the gather
+        assemble_gather(ctx, S->xy, S->n0, S->n1, S->n2, elist_p, El, N, K, &st.ms_sort, &st.ms_reduce);
+        elist.release();
+    } else {
+        DevBuf<double> kblk(ctx, El * 36);
+        if (El)
+            MAG_LAUNCH(ctx, element_stiffness_kernel, cdiv(El, kElemThreads), kElemThreads, 0,
+                       (const double2 *)S->xy.p, (const uint32_t *)S->n0.p, (const uint32_t *)S->n1.p,
+                       (const uint32_t *)S->n2.p, elist_p, El, 1, kblk.p);
+        st.ms_elem = phase.stop();
+
+        // ---- COO keys + stable sort ----------------------------------------------
+        phase.start();
+        const size_t n_keys = El * 9;
+        const int bits = bits_for(N + 1);
+        DevBuf<uint64_t> keys(ctx, n_keys), keys_alt(ctx, n_keys);
+        DevBuf<uint32_t> pay(ctx, n_keys), pay_alt(ctx, n_keys);
+        if (El) {
+            MAG_LAUNCH(ctx, emit_keys_kernel, cdiv(El, 256), 256, 0, (const uint32_t *)S->n0.p,
+                       (const uint32_t *)S->n1.p, (const uint32_t *)S->n2.p, elist_p, El, bits, S->node_lo,
+                       S->node_hi, keys.p, pay.p);
+            radix_sort_pairs(ctx, keys.p, pay.p, keys_alt.p, pay_alt.p, n_keys, 2 * bits);
+        }
+        keys_alt.release();
+        pay_alt.release();
+        elist.release();
+        st.ms_sort = phase.stop();
+
+        // ---- segmented reduction into BSR ------------------------------------------
+        phase.start();
+        K.browptr.alloc(ctx, (size_t)n_own + 1);
+        K.browptr.zero();
+        {
+            DevBuf<uint32_t> head(ctx, n_keys + 1);
+            if (n_keys)
+                MAG_LAUNCH(ctx, mark_heads_kernel, cdiv(n_keys, 256), 256, 0, (const uint64_t *)keys.p,
+                           n_keys, bits, K.node_lo, head.p, K.browptr.p);
+            DevBuf<uint32_t> uid(ctx, n_keys + 1);      // exclusive scan of head; uid[n_keys] = #blocks
+            exclusive_scan_u32(ctx, head.p, n_keys, uid.p, n_keys + 1);
+            exclusive_scan_u32(ctx, K.browptr.p, n_own, K.browptr.p, (size_t)n_own + 1);
+            K.n_blocks = read_u32(ctx, uid.p + n_keys);
+            K.bcol.alloc(ctx, K.n_blocks);
+            K.bval.alloc(ctx, (size_t)K.n_blocks * 4);
+            if (n_keys)
+                MAG_LAUNCH(ctx, segment_reduce_kernel, cdiv(n_keys, 256), 256, 0, (const uint64_t *)keys.p,
+                           (const uint32_t *)pay.p, (const uint32_t *)head.p, (const uint32_t *)uid.p,
+                           n_keys, bits, (const double *)kblk.p, K.bcol.p, K.bval.p);
+        }
+        keys.release();
+        pay.release();
+        kblk.release();
+        st.ms_reduce = phase.stop();
     }
-    keys.release();
-    pay.release();
-    kblk.release();
     st.nnz_structural = (uint64_t)K.n_blocks * 4;
-    st.ms_reduce = phase.stop();
 
     // ---- Dirichlet elimination (solver.rs:340-432, 126-137) --------------------
     phase.start();

@@ -48,7 +48,7 @@ pub mod sys {
         pub want_sigma: i32,
         pub allreduce: i32,
         pub coarse_aggregates: i32,
-        pub reserved: i32,
+        pub assembly: i32,
         pub stream: *mut c_void,
     }
     #[repr(C)]
