@@ -2,7 +2,6 @@
 assembly leaves — the full K, K_ff, the rhs and the DOF maps bit for bit — hence bit-identical solves, for
 whole meshes and for the row blocks of the partitioned path.  The per-node core is also checked against the
 oracle on the CPU (tests/test_gather_core_host.py); the default path against the oracle in test_gpu_parity.py."""
-import os
 from pathlib import Path
 
 import numpy as np
@@ -11,9 +10,7 @@ import pytest
 from magnetite_b200 import _lib, meshgen, solver
 from magnetite_b200.datatypes import MeshSoA
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MAGNETITE_B200_TEST_GATHER") != "1",
-                                 reason="gather assembly: opt-in path, enable with MAGNETITE_B200_TEST_GATHER=1")]
+pytestmark = pytest.mark.gpu
 META = meshgen.EXAMPLE_MATERIAL
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
