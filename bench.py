@@ -298,6 +298,29 @@ def run_ours(args):
                                   "achieved": iter_bytes / (ms_iter * 1e-3) / 1e9,
                                   "frac": iter_bytes / (ms_iter * 1e-3) / 1e9 / peak}}
 
+    # ---- extra: the opt-in gather assembly beside the default, same mesh, same timers ---------
+    # Single GPU only (mag_system_free is collective on several ranks); it can never break the line above it.
+    gather = None
+    if world == 1:
+        try:
+            optg = _lib.default_options(stream=stream.cuda_stream, allreduce=args.allreduce,
+                                        spmv_format=args.spmv_format, assembly=1)
+            g_ms, g_st = [], None
+            for _ in range(3):
+                gsys, g_st = C.c_void_p(), _lib.MagStats()
+                _lib.check(lib.mag_assemble(ctx.handle, C.byref(view), C.byref(mat), C.byref(optg), C.byref(gsys),
+                                            C.byref(g_st)), "mag_assemble(gather)")
+                lib.mag_system_free(gsys)
+                g_ms.append(g_st.ms_elem + g_st.ms_sort + g_st.ms_reduce + g_st.ms_bc)
+            ms_g = statistics.mean(g_ms[1:])           # the first one pays the kernels' first launch
+            gather = {"assembly": "gather (mag_options.assembly = 1): same K bit for bit, opt-in this round",
+                      "assembly_melem_s": E / (ms_g * 1e-3) / 1e6, "assembly_ms": ms_g,
+                      "ms_incidence_sort": g_st.ms_sort, "ms_count_fill": g_st.ms_reduce, "ms_bc": g_st.ms_bc,
+                      "same_counts_as_default": (int(g_st.nnz), int(g_st.nnz_structural), int(g_st.n_free))
+                                                == (int(st.nnz), int(st.nnz_structural), int(st.n_free))}
+        except Exception as err:                       # an extra metric must not cost the benchmark line
+            gather = {"error": str(err)}
+
     # ---- extra: the same system through the opt-in two-level preconditioner ----------
     two_level = None
     if not args.no_two_level:
@@ -400,7 +423,7 @@ def run_ours(args):
                     "pcg_final_rel_residual": last.final_residual / last.b_norm if last.b_norm else 0.0,
                     "spmv_hbm_gbs": achieved, "ms_elem": last.ms_elem, "ms_sort": last.ms_sort,
                     "ms_reduce": last.ms_reduce, "ms_bc": last.ms_bc, "ms_format": last.ms_format,
-                    "ms_post": last.ms_post, "two_level": two_level,
+                    "ms_post": last.ms_post, "gather_assembly": gather, "two_level": two_level,
                     # device-side timeline of one PCG iteration on rank 0 (%globaltimer, us): update_p + launch gap,
                     # spmv, gap, wait for global p.q, update_xr (incl. wait), gap, wait for global r.z
                     "pcg_iteration_timeline_us": [round(v / 1e3, 2) for v in list(last.prof)[:7]]},
