@@ -1,0 +1,52 @@
+"""The benchmark contract, as far as it can be checked without a GPU: the reference arm (`bench.py --impl
+reference`, the oracle port timed on host cores) prints ONE JSON line with the keys the driver reads; ranks
+other than 0 stay silent; the GPU arm refuses to run without a device instead of falling back to the CPU."""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+BENCH = [sys.executable, str(ROOT / "bench.py")]
+
+
+def _env(**extra):
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env.update(extra)
+    return env
+
+
+def test_reference_arm_prints_one_contract_line(built):
+    r = subprocess.run(BENCH + ["--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "1", "--ref-nx", "40",
+                                "--ref-ny", "20"], capture_output=True, text=True, timeout=600, env=_env(), cwd=ROOT)
+    assert r.returncode == 0, r.stderr
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1
+    assert d["unit"] == "Melem/s" and d["higher_is_better"] is True and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert d["vs_baseline"] is None and d["scaling"] in ("weak", "strong") and d["value"] > 0 and d["ms_per_step"] > 0
+    assert "4000x2000" in d["config"]["workload"] and "40x20" in d["config"]["sample"]      # our arm's workload, a bounded sample of it
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == d["value"] and cb["unit"] == d["unit"] and cb["sample"]
+    assert cb["faithful_dense"]["cg_iters"] > 0 and cb["faithful_dense"]["seconds"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0                                                              # nothing of ours ran on a GPU
+
+
+def test_reference_arm_is_silent_on_other_ranks(built):
+    r = subprocess.run(BENCH + ["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"], capture_output=True,
+                       text=True, timeout=120, env=_env(RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), cwd=ROOT)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_gpu_arm_has_no_cpu_fallback(built):
+    import torch
+    import pytest
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run(BENCH + ["--steps", "1", "--warmup", "3", "--nx", "16", "--ny", "8"], capture_output=True, text=True,
+                       timeout=300, env=_env(), cwd=ROOT)
+    assert r.returncode != 0
+    assert not any(ln.lstrip().startswith("{") for ln in r.stdout.splitlines())              # no benchmark line was produced
