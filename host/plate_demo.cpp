@@ -2,6 +2,7 @@
 // build Vec<Node>/Vec<Element> (mesher defaults + tensile boundary rules), solver::run,
 // post_processor::csv_output.   usage: plate_demo NX NY nodes.csv elements.csv
 //                                      plate_demo --format-selftest      (no GPU needed)
+//                                      plate_demo --format-stdin         hex bit patterns in, formatted f64 out (no GPU needed)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -36,8 +37,22 @@ static int format_selftest() {
     return bad;
 }
 
+// one hexadecimal 64-bit pattern per input line -> the f64 with those bits, formatted like Rust's `{}`
+static int format_stdin() {
+    char line[64];
+    while (std::fgets(line, sizeof line, stdin)) {
+        const unsigned long long bits = std::strtoull(line, nullptr, 16);
+        double v;
+        static_assert(sizeof v == sizeof bits, "f64 is 64 bits");
+        std::memcpy(&v, &bits, sizeof v);
+        std::printf("%s\n", post_processor::format_f64(v).c_str());
+    }
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc == 2 && !std::strcmp(argv[1], "--format-selftest")) return format_selftest();
+    if (argc == 2 && !std::strcmp(argv[1], "--format-stdin")) return format_stdin();
     if (argc != 5) { std::fprintf(stderr, "usage: plate_demo NX NY nodes.csv elements.csv\n"); return 2; }
     const std::size_t nx = std::strtoul(argv[1], nullptr, 10), ny = std::strtoul(argv[2], nullptr, 10);
     const double h = 2.0;

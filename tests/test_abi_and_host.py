@@ -166,6 +166,17 @@ def test_cpp_host_layer_formats_like_rust(built):
     subprocess.run(["make", "-C", str(ROOT / "host")], check=True, capture_output=True)
     r = subprocess.run([str(exe), "--format-selftest"], capture_output=True, text=True)
     assert r.returncode == 0 and "FORMAT_OK" in r.stdout, r.stdout + r.stderr
+    # the C++ formatter is its own implementation: random bit patterns (every exponent, subnormals, both zeros,
+    # NaN and the infinities) against the Python mirror
+    rng = np.random.default_rng(17)
+    bits = np.concatenate([rng.integers(0, 2 ** 64, 4000, dtype=np.uint64),
+                           np.array([0, 1 << 63, 1, 0x7FF0000000000000, 0xFFF0000000000000, 0x7FF8000000000000,
+                                     0x7FEFFFFFFFFFFFFF, 0x0010000000000000, 0x000FFFFFFFFFFFFF], np.uint64)])
+    r = subprocess.run([str(exe), "--format-stdin"], input="".join(f"{int(b):016x}\n" for b in bits), capture_output=True, text=True)
+    got = r.stdout.splitlines()
+    assert r.returncode == 0 and len(got) == len(bits)
+    for text, v in zip(got, bits.view(np.float64)):
+        assert text == post_processor.rust_f64_display(float(v)), (hex(int(np.float64(v).view(np.uint64))), text)
 
 
 def test_stress_strain_matrix_matches_oracle(built):
@@ -226,3 +237,33 @@ def test_library_csv_writer_matches_python_writer(tmp_path, built):
             writer(x, y, ux, uy, n0, n1, n2, stress, str(tmp_path / "no" / "n.csv"), str(tmp_path / "e.csv"))
         with pytest.raises(MagnetiteError, match=want.replace("nodes", "elements")):
             writer(x, y, ux, uy, n0, n1, n2, stress, str(tmp_path / "n.csv"), str(tmp_path / "no" / "e.csv"))
+
+
+def test_format_f64_properties_over_all_finite_doubles(built):
+    """Rust's `{}` for f64 as the CSV contract needs it (post_processor.rs:44-75), fuzzed over the whole double
+    range: the library's formatter agrees with the Python mirror, the text parses back to the same bits,
+    never uses an exponent, never ends in '.0', and carries the sign of negative zero."""
+    import ctypes as C
+    import math
+    import struct
+    from hypothesis import given, settings, strategies as st
+    lib = _lib.load()
+    buf = C.create_string_buffer(512)
+
+    @settings(max_examples=3000, deadline=None)
+    @given(st.floats(allow_nan=False, allow_infinity=False, width=64))
+    def check(v):
+        n = lib.mag_format_f64(v, buf)
+        text = buf.value.decode()
+        assert n == len(text) and text == post_processor.rust_f64_display(v)
+        assert struct.pack("<d", float(text)) == struct.pack("<d", v)
+        assert "e" not in text.lower() and not text.endswith(".0") and not text.endswith(".")
+        assert text.startswith("-") == (math.copysign(1.0, v) < 0)
+        assert n <= 330                       # "-0." + 323 zeros + 17 digits at most: inside the 400-byte contract
+
+    check()
+    # powers of ten and their neighbours: where digit counts and the decimal point position change
+    for e in range(-323, 309):
+        for v in (float(f"1e{e}"), np.nextafter(float(f"1e{e}"), np.inf), np.nextafter(float(f"1e{e}"), -np.inf)):
+            lib.mag_format_f64(float(v), buf)
+            assert buf.value.decode() == post_processor.rust_f64_display(float(v)) and float(buf.value) == float(v)
