@@ -267,3 +267,76 @@ def test_format_f64_properties_over_all_finite_doubles(built):
         for v in (float(f"1e{e}"), np.nextafter(float(f"1e{e}"), np.inf), np.nextafter(float(f"1e{e}"), -np.inf)):
             lib.mag_format_f64(float(v), buf)
             assert buf.value.decode() == post_processor.rust_f64_display(float(v)) and float(buf.value) == float(v)
+
+
+def _random_input_json(rng):
+    """A random input.json: usually valid, sometimes broken in one of the ways mesher.rs:713-930 rejects."""
+    def num():
+        kind = int(rng.integers(0, 3))
+        if kind == 0:
+            return float(rng.integers(-50, 50))                                   # "12.0"
+        if kind == 1:
+            return round(float(rng.normal()) * 10.0 ** int(rng.integers(-3, 4)), 6)   # "-0.004217", "1830.25"
+        return int(rng.integers(-5, 5))                                           # a JSON integer
+    md = {"part_thickness": abs(num()) + 0.1, "material_elasticity": 69e9, "poisson_ratio": 0.33,
+          "characteristic_length_min": 0, "characteristic_length_max": 0.3}
+    rules = {}
+    for i in range(int(rng.integers(0, 4))):
+        region = {}
+        for axis in "xy":
+            lo, hi = sorted([num(), num()])
+            if rng.random() < 0.7: region[f"{axis}_target_min"] = lo
+            if rng.random() < 0.7: region[f"{axis}_target_max"] = hi
+        tx = {"ux": num(), "fx": None} if rng.random() < 0.5 else {"ux": None, "fx": num()}
+        ty = {"uy": num(), "fy": None} if rng.random() < 0.5 else {"uy": None, "fy": num()}
+        rules[f"rule{i}"] = {"region": region, "targets": {**tx, **ty}}
+    data = {"metadata": md, "boundary_conditions": rules}
+    fault = rng.integers(0, 14)
+    first = next(iter(rules), None)
+    if fault == 0: del data["metadata"]
+    elif fault == 1: del data["boundary_conditions"]
+    elif fault == 2: del md[rng.choice(["part_thickness", "material_elasticity", "poisson_ratio"])]
+    elif fault == 3: md[rng.choice(["characteristic_length_min", "characteristic_length_max"])] = "fine"
+    elif fault == 4 and first: del rules[first]["region"]
+    elif fault == 5 and first: del rules[first]["targets"]
+    elif fault == 6 and first: rules[first]["region"]["x_target_min"] = "left"
+    elif fault == 7 and first: rules[first]["region"].update(y_target_min=5, y_target_max=-5)
+    elif fault == 8 and first: rules[first]["targets"].update(ux=1.0, fx=2.0)
+    elif fault == 9 and first: rules[first]["targets"].update(uy=None, fy=None)
+    return data
+
+
+def test_cpp_and_python_input_semantics_agree_on_random_files(tmp_path, built):
+    """Differential test of the two host mirrors of load_input_file / parse_input_metadata / the boundary-rule
+    validation (mesher.rs:713-930): same parsed values on valid files, same error text on rejected ones."""
+    import json
+    import subprocess
+    subprocess.run(["make", "-C", str(ROOT / "host")], check=True, capture_output=True)
+    exe = str(ROOT / "host" / "magnetite_b200")
+    f = post_processor.rust_f64_display
+    o = lambda v: "None" if v is None else f(v)          # noqa: E731
+    rng = np.random.default_rng(2024)
+    outcomes = set()
+    for case in range(80):
+        path = tmp_path / f"in{case}.json"
+        path.write_text(json.dumps(_random_input_json(rng)))
+        try:
+            data = mesher.load_input_file(str(path))
+            meta = mesher.parse_input_metadata(data)
+            want = [f"metadata {f(meta.youngs_modulus)} {f(meta.poisson_ratio)} {f(meta.part_thickness)} "
+                    f"{f(meta.characteristic_length_min)} {f(meta.characteristic_length_max)}"]
+            for rule in mesher.parse_boundary_rules(data):
+                g, tg = rule.region, rule.target
+                want.append(f"rule {rule.name} region {f(g.x_min)} {f(g.x_max)} {f(g.y_min)} {f(g.y_max)} "
+                            f"targets {o(tg.ux)} {o(tg.uy)} {o(tg.fx)} {o(tg.fy)}")
+            error = None
+        except MagnetiteError as err:
+            error = str(err)
+        r = subprocess.run([exe, "--dump-rules", str(path)], capture_output=True, text=True)
+        if error is None:
+            assert r.returncode == 0 and r.stdout.splitlines() == want, (case, path.read_text(), r.stdout, r.stderr)
+            outcomes.add("ok")
+        else:
+            assert r.returncode == 1 and r.stderr.strip() == f"Received error: {error}", (case, path.read_text(), r.stderr, error)
+            outcomes.add(re.sub(r"rule\d|'[^']*'|\b[xy]_target_\w+", "*", error))
+    assert "ok" in outcomes and len(outcomes) >= 7, outcomes    # valid files and at least six different rejections
