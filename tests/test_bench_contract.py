@@ -31,6 +31,8 @@ def test_reference_arm_prints_one_contract_line(built):
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == d["value"] and cb["unit"] == d["unit"] and cb["sample"]
     assert cb["faithful_dense"]["cg_iters"] > 0 and cb["faithful_dense"]["seconds"] > 0
+    ac = cb["all_cores"]                        # extra figure: the same sample with the CG on every host core
+    assert ac["threads"] >= 1 and ac["value"] > 0 and ac["unit"] == d["unit"] and "not the reference" in ac["note"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0                                                              # nothing of ours ran on a GPU
 

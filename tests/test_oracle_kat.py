@@ -195,3 +195,26 @@ def test_oracle_reproduces_golden(name):
     for k in ("ux", "uy", "fx", "fy", "stress"):
         assert np.array_equal(r[k], g[k]), k
     assert r["stats"]["iters"] == int(g["iters"][0])
+
+
+def test_all_cores_pcg_agrees_with_the_sequential_port():
+    """oracle_mt (bench infrastructure: the port's Jacobi-PCG on pthreads) reaches the port's solution in the
+    port's iteration count, for any thread count, and is deterministic for a given one."""
+    from oracle import oracle_mt as MT
+    mesh = meshgen.jitter(meshgen.plate(60, 30))
+    om = O.Mesh(mesh)
+    csr, rhs, fmap = O.partition(om, O.assemble_sparse(om, O.element_stiffness(om, META)), dense=False)
+    x_ref, it_ref, _ = O.cg(csr, rhs, O.cg_options(jacobi=1, rel_tol=1e-10))
+    for threads in (1, 3, 8, 10_000):                      # absurd thread counts are clamped (>= 64 rows each)
+        x, it, res = MT.pcg(csr, rhs, rel_tol=1e-10, threads=threads)
+        assert abs(it - it_ref) <= 2
+        assert np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref) < 1e-9
+        assert res <= 1e-10 * np.linalg.norm(rhs)
+    a, _, _ = MT.pcg(csr, rhs, threads=4)
+    b, _, _ = MT.pcg(csr, rhs, threads=4)
+    assert np.array_equal(a, b)
+    # a zero right-hand side needs no iteration; an empty system is legal
+    x0, it0, _ = MT.pcg(csr, np.zeros_like(rhs), threads=4)
+    assert it0 == 0 and not x0.any()
+    xe, ite, _ = MT.pcg((np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(0)), np.zeros(0), threads=4)
+    assert xe.size == 0 and ite == 0
