@@ -36,3 +36,29 @@ def ctx(built):
 def material():
     from magnetite_b200 import meshgen
     return meshgen.EXAMPLE_MATERIAL
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _assembly_override():
+    """MAGNETITE_B200_TEST_ASSEMBLY=1 runs every test that builds its options through the Python binding with the
+    gather assembly (mag_options.assembly = 1) unless the test sets the field itself: the whole parity suite
+    against the opt-in path with one command.  Unset (the default) nothing changes."""
+    import os
+    want = os.environ.get("MAGNETITE_B200_TEST_ASSEMBLY")
+    if want is None:
+        yield
+        return
+    from magnetite_b200 import _lib, solver
+    original = _lib.default_options
+
+    def patched(**overrides):
+        overrides.setdefault("assembly", int(want))
+        return original(**overrides)
+
+    _lib.default_options = patched
+    solver.default_options = patched
+    try:
+        yield
+    finally:
+        _lib.default_options = original
+        solver.default_options = original
