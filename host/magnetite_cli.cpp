@@ -4,6 +4,11 @@
 //                                                      -> nodes.csv, elements.csv in the working directory
 //   magnetite_b200 input.json geom.msh --reorder       the same with the nodes renumbered (reverse Cuthill-McKee)
 //                                                      around the solve; the CSVs keep the mesh file's numbering
+//   magnetite_b200 input.json outline.csv [holes.csv ...]   the reference's own form (main.rs:21-40): CSV outlines
+//                                                      -> geom.geo -> `gmsh geom.geo -2 -o geom.msh` -> the same flow;
+//                                                      needs a gmsh binary on PATH (SVG outlines: Python mirror)
+//   magnetite_b200 --geo out.geo input.json outline.csv [holes.csv ...]   write the gmsh script only (no GPU, no gmsh)
+//   magnetite_b200 --mesh out.msh input.json outline.csv [holes.csv ...]  run gmsh on it and keep the mesh (no GPU)
 //   magnetite_b200 --dump-rules input.json             print the parsed metadata and boundary rules (no GPU)
 //   magnetite_b200 --band geom.msh                     node band of the mesh as numbered and after RCM (no GPU)
 //
@@ -55,22 +60,57 @@ int main(int argc, char **argv) {
                         (unsigned long long)before, (unsigned long long)after);
             return 0;
         }
+        auto ends_with = [](const std::string &t, const char *suffix) {
+            const size_t n = std::strlen(suffix);
+            return t.size() >= n && t.compare(t.size() - n, n, suffix) == 0;
+        };
+        // mesher.rs:946-959: every .csv adds one container (the first is the outer loop); anything else is an error
+        auto read_outlines = [&](int first, int last) {
+            std::vector<std::vector<Vertex>> containers;
+            for (int i = first; i < last; ++i) {
+                const std::string geom = argv[i];
+                if (geom.rfind("--", 0) == 0) continue;
+                if (ends_with(geom, ".csv")) containers.push_back(mesher::parse_csv(geom));
+                else throw MagnetiteError(MagnetiteError::Kind::Input, "Unrecognized geometry filetype " + geom +
+                                          (ends_with(geom, ".svg") ? " (SVG outlines are read by the Python mirror)" : ""));
+            }
+            return containers;
+        };
+        if (argc >= 5 && !std::strcmp(argv[1], "--geo")) {
+            const ModelMetadata md = mesher::parse_input_metadata(mesher::load_input_file(argv[3]));
+            mesher::build_geo(read_outlines(4, argc), argv[2], md.characteristic_length_min, md.characteristic_length_max);
+            return 0;
+        }
+        if (argc >= 5 && !std::strcmp(argv[1], "--mesh")) {                      // outlines -> gmsh -> out.msh, nothing else
+            const ModelMetadata md = mesher::parse_input_metadata(mesher::load_input_file(argv[3]));
+            mesher::compute_mesh(read_outlines(4, argc), argv[2], md.characteristic_length_min, md.characteristic_length_max);
+            std::vector<Node> nodes;
+            std::vector<Element> elements;
+            mesher::parse_mesh(argv[2], nodes, elements);
+            std::printf("nodes %zu elements %zu\n", nodes.size(), elements.size());
+            return 0;
+        }
         if (argc < 3) {
-            std::fprintf(stderr, "usage: magnetite_b200 input.json geom.msh [--skip] [--reorder]\n");
+            std::fprintf(stderr, "usage: magnetite_b200 input.json geom.msh|outline.csv... [--skip] [--reorder]\n");
             return 2;
         }
         SolverOptions so;
         for (int i = 3; i < argc; ++i)
             if (!std::strcmp(argv[i], "--reorder")) so.reorder = true;
-        const std::string input_file = argv[1], mesh_file = argv[2];
-        if (mesh_file.size() < 4 || mesh_file.substr(mesh_file.size() - 4) != ".msh")
-            throw MagnetiteError(MagnetiteError::Kind::Input,
-                                 "Unrecognized geometry filetype " + mesh_file + " (run gmsh on the outline first and pass the .msh)");
+        const std::string input_file = argv[1];
+        std::string mesh_file = argv[2];
         const Json j = mesher::load_input_file(input_file);                     // mesher.rs:943-944
         const ModelMetadata md = mesher::parse_input_metadata(j);
+        const bool from_outlines = !ends_with(mesh_file, ".msh");
+        if (from_outlines) {                                                     // mesher.rs:946-967
+            const std::vector<std::vector<Vertex>> containers = read_outlines(2, argc);
+            mesh_file = "geom.msh";
+            mesher::compute_mesh(containers, mesh_file, md.characteristic_length_min, md.characteristic_length_max);
+        }
         std::vector<Node> nodes;
         std::vector<Element> elements;
         mesher::parse_mesh(mesh_file, nodes, elements);                          // mesher.rs:969
+        if (from_outlines) std::remove(mesh_file.c_str());                       // mesher.rs:701
         mesher::check_ccw(elements, solver::element_areas(elements, nodes));     // mesher.rs:691-693
         std::printf("info: loaded %zu nodes and %zu elements\n", nodes.size(), elements.size());
         mesher::apply_boundary_conditions(j, nodes, false);                      // mesher.rs:971

@@ -166,12 +166,13 @@ double compute_element_area(const Element &element, const std::vector<Node> &nod
 
 namespace post_processor {
 
-std::string format_f64(double v) {
+// Rust's `{}` for a float of type T: the SHORTEST digits that round-trip in that type, positional, zero padded
+// (1.2345678901234567e25 -> "12345678901234567000000000"); to_chars(fixed) would print the exact binary
+// expansion instead, so take the shortest digits from the scientific form and place the point by hand.
+template <class T>
+static std::string format_shortest(T v) {
     if (std::isnan(v)) return "NaN";
     if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
-    // Rust prints the SHORTEST round-trip digits and pads with zeros (1.2345678901234567e25 ->
-    // "12345678901234567000000000"); to_chars(fixed) would print the exact binary expansion instead,
-    // so take the shortest digits from the scientific form and place the point by hand.
     char buf[64];
     const auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);
     std::string s(buf, r.ptr), out;
@@ -190,6 +191,9 @@ std::string format_f64(double v) {
     }
     return out;
 }
+
+std::string format_f64(double v) { return format_shortest<double>(v); }
+std::string format_f32(float v) { return format_shortest<float>(v); }
 
 // Rust's Display of std::io::Error, which the reference embeds in its message (post_processor.rs:27-29)
 static std::string os_error(int err) { return std::string(std::strerror(err)) + " (os error " + std::to_string(err) + ")"; }

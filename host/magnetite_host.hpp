@@ -64,6 +64,7 @@ double compute_element_area(const Element &element, const std::vector<Node> &nod
 namespace post_processor {
 // Rust's `{}` for f64: shortest round-trip decimal, never scientific, no ".0" on integral values.
 std::string format_f64(double v);
+std::string format_f32(float v);      // the same for f32 (the characteristic lengths of ModelMetadata)
 void csv_output(const std::vector<Element> &elements, const std::vector<Node> &nodes,
                 const std::string &nodes_output, const std::string &elements_output, bool quiet = false);
 }  // namespace post_processor

@@ -1,10 +1,17 @@
 // magnetite_io.cpp — see magnetite_io.hpp.
 #include "magnetite_io.hpp"
 
+#include <fcntl.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <algorithm>
 #include <cctype>
+#include <cerrno>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <limits>
 #include <sstream>
@@ -108,6 +115,9 @@ std::optional<double> Json::as_f64() const {
 // mesher
 // ---------------------------------------------------------------------------
 namespace mesher {
+
+// Rust's Display of std::io::Error
+static std::string os_error_text(int err) { return std::string(std::strerror(err)) + " (os error " + std::to_string(err) + ")"; }
 
 Json load_input_file(const std::string &input_file) {          // mesher.rs:713-760
     std::ifstream f(input_file);
@@ -245,6 +255,150 @@ void parse_mesh(const std::string &mesh_file, std::vector<Node> &nodes, std::vec
 void check_ccw(std::vector<Element> &elements, const std::vector<double> &areas) {     // mesher.rs:522-526
     for (size_t e = 0; e < elements.size(); ++e)
         if (areas[e] < 1.0) std::swap(elements[e].nodes[0], elements[e].nodes[2]);
+}
+
+std::vector<Vertex> parse_csv(const std::string &csv_file) {              // mesher.rs:253-299
+    std::ifstream in(csv_file, std::ios::binary);
+    if (!in) throw MagnetiteError(MagnetiteError::Kind::Input, "Unable to open csv file " + csv_file);
+    std::stringstream ss;
+    ss << in.rdbuf();
+    const std::string contents = ss.str();
+    auto trim = [](std::string t) {                     // str::trim: Unicode white space; ASCII is what CSVs hold
+        const char *ws = " \t\r\n\v\f";
+        const size_t a = t.find_first_not_of(ws);
+        if (a == std::string::npos) return std::string();
+        return t.substr(a, t.find_last_not_of(ws) - a + 1);
+    };
+    auto split = [&](const std::string &line) {
+        std::vector<std::string> cells;
+        size_t start = 0;
+        for (;;) {
+            const size_t comma = line.find(',', start);
+            cells.push_back(trim(line.substr(start, comma == std::string::npos ? std::string::npos : comma - start)));
+            if (comma == std::string::npos) break;
+            start = comma + 1;
+        }
+        return cells;
+    };
+    std::vector<Vertex> vertices;
+    bool have_header = false;
+    size_t xi = 0, yi = 0, pos = 0;
+    while (pos <= contents.size()) {
+        const size_t nl = contents.find('\n', pos);
+        const std::string line = contents.substr(pos, nl == std::string::npos ? std::string::npos : nl - pos);
+        pos = (nl == std::string::npos) ? contents.size() + 1 : nl + 1;
+        if (line.empty()) continue;
+        const std::vector<std::string> cells = split(line);
+        if (!have_header) {
+            const auto fx = std::find(cells.begin(), cells.end(), "x"), fy = std::find(cells.begin(), cells.end(), "y");
+            if (fx == cells.end() || fy == cells.end())
+                throw MagnetiteError(MagnetiteError::Kind::Input, "Error in csv file: Missing x and/or y field");
+            xi = (size_t)(fx - cells.begin()); yi = (size_t)(fy - cells.begin());
+            have_header = true;
+            continue;
+        }
+        std::vector<double> vals;
+        for (const std::string &c : cells) {
+            char *end = nullptr;
+            const double v = std::strtod(c.c_str(), &end);
+            if (c.empty() || end != c.c_str() + c.size())                      // the reference panics (expect)
+                throw MagnetiteError(MagnetiteError::Kind::Input, "Non-float value in csv points");
+            vals.push_back(v);
+        }
+        if (xi >= vals.size() || yi >= vals.size())                            // the reference panics (index)
+            throw MagnetiteError(MagnetiteError::Kind::Input, "Non-float value in csv points");
+        vertices.push_back(Vertex{vals[xi], vals[yi]});
+    }
+    return vertices;
+}
+
+std::string geo_text(const std::vector<std::vector<Vertex>> &vc, float cl_min, float cl_max) {   // mesher.rs:305-472
+    if (vc.empty()) throw MagnetiteError(MagnetiteError::Kind::Input, "no geometry was given");   // the reference panics
+    const auto f = post_processor::format_f64;
+    auto point = [&](size_t id, const Vertex &v) {
+        return "Point(" + std::to_string(id) + ") = { " + f(v.x) + ", " + f(v.y) + ", 0, 1.0 };\n";
+    };
+    std::string out = "// Define outer points\n";
+    for (size_t i = 0; i < vc[0].size(); ++i) out += point(i, vc[0][i]);
+    out += "\n// Define inner points\n";
+    size_t offset = vc[0].size();
+    std::vector<size_t> inner_offsets{0};
+    for (size_t c = 1; c < vc.size(); ++c) {
+        inner_offsets.push_back(offset);
+        for (size_t i = 0; i < vc[c].size(); ++i) out += point(i + offset, vc[c][i]);
+        offset += vc[c].size();
+    }
+    out += "\n// Connect points\n";
+    auto line = [](size_t id, size_t a, size_t b) {
+        return "Line(" + std::to_string(id) + ") = { " + std::to_string(a) + ", " + std::to_string(b) + " };\n";
+    };
+    for (size_t c = 0; c < vc.size(); ++c) {
+        out += "\n// Point connections for surface " + std::to_string(c) + "\n";
+        const size_t off = inner_offsets[c], n = vc[c].size();
+        for (size_t k = 1; k < n; ++k) out += line(k + off - 1, k + off - 1, k + off);
+        out += line(n + off - 1, n + off - 1, off);
+    }
+    out += "\n//Register loops\n";
+    for (size_t c = 0; c < vc.size(); ++c) {
+        out += "Line Loop(" + std::to_string(c + 1) + ") = {";
+        for (size_t k = 0; k < vc[c].size(); ++k) out += std::string(k ? "," : "") + " " + std::to_string(k + inner_offsets[c]);
+        out += " };\n";
+    }
+    out += "\n//Define surface\nPlane Surface(1) = {";
+    for (size_t k = 0; k < vc.size(); ++k) {                                   // mesher.rs:424-430
+        const size_t loop = vc.size() > 2 ? k : vc.size() - 1 - k;
+        out += std::string(k ? "," : "") + " " + std::to_string(loop + 1);
+    }
+    out += " };\n";
+    out += "\n// Define Mesh Settings\nMesh.ElementOrder = 1;\nMesh.Algorithm  = 1;\nMesh.CharacteristicLengthMin = " +
+           post_processor::format_f32(cl_min) + ";\nMesh.CharacteristicLengthMax = " + post_processor::format_f32(cl_max) +
+           ";\nMesh 2;\n";
+    return out;
+}
+
+void build_geo(const std::vector<std::vector<Vertex>> &vc, const std::string &output_file, float cl_min, float cl_max) {
+    const std::string text = geo_text(vc, cl_min, cl_max);
+    std::ofstream out(output_file, std::ios::binary | std::ios::trunc);
+    if (!out) throw MagnetiteError(MagnetiteError::Kind::Mesher, "Failed to create .geo file");   // the reference panics
+    out << text;
+}
+
+void compute_mesh(const std::vector<std::vector<Vertex>> &vertices, const std::string &output, float cl_min, float cl_max,
+                  bool quiet) {                                                // mesher.rs:481-519
+    const std::string geo_filepath = "geom.geo";
+    if (!quiet) std::printf("info: building .geo for Gmsh with %.3f< CL < %.3f\n", (double)cl_min, (double)cl_max);
+    build_geo(vertices, geo_filepath, cl_min, cl_max);
+    if (!quiet) std::printf("info: running gmsh...\n");
+    std::fflush(stdout);
+    // fork/exec with a close-on-exec pipe: the child reports errno through it only if exec itself fails
+    int report[2];
+    if (pipe2(report, O_CLOEXEC) != 0) throw MagnetiteError(MagnetiteError::Kind::Mesher, "Gmsh failed: " + os_error_text(errno));
+    const pid_t pid = fork();
+    if (pid < 0) {
+        const int err = errno;
+        close(report[0]); close(report[1]);
+        throw MagnetiteError(MagnetiteError::Kind::Mesher, "Gmsh failed: " + os_error_text(err));
+    }
+    if (pid == 0) {                                                            // child: gmsh geom.geo -2 -o <output>, output discarded
+        const int devnull = open("/dev/null", O_WRONLY);
+        if (devnull >= 0) { dup2(devnull, 1); dup2(devnull, 2); }
+        execlp("gmsh", "gmsh", geo_filepath.c_str(), "-2", "-o", output.c_str(), (char *)nullptr);
+        const int err = errno;
+        if (write(report[1], &err, sizeof err) < 0) {}
+        _exit(127);
+    }
+    close(report[1]);
+    int exec_errno = 0;
+    ssize_t got;
+    while ((got = read(report[0], &exec_errno, sizeof exec_errno)) < 0 && errno == EINTR) {}
+    close(report[0]);
+    int status = 0;
+    while (waitpid(pid, &status, 0) < 0 && errno == EINTR) {}
+    // Only a gmsh that could not be STARTED is an error (mesher.rs:503-513); its exit status is ignored and a
+    // failed meshing run surfaces in parse_mesh ("Unable to open auto-generated mesh file").
+    if (got == (ssize_t)sizeof exec_errno)
+        throw MagnetiteError(MagnetiteError::Kind::Mesher, "Gmsh failed: " + os_error_text(exec_errno));
+    std::remove(geo_filepath.c_str());
 }
 
 }  // namespace mesher

@@ -5,6 +5,9 @@
 //   mesher::apply_boundary_conditions                <- src/mesher.rs:815-930 (strict > / <, later rules win)
 //   mesher::parse_mesh                               <- src/mesher.rs:536-704 (MSH 4.x ASCII)
 //   mesher::check_ccw                                <- src/mesher.rs:522-526 (flips when area < 1.0)
+//   mesher::parse_csv                                <- src/mesher.rs:253-299 (outline vertices, x / y columns)
+//   mesher::geo_text / build_geo / compute_mesh      <- src/mesher.rs:305-519 (.geo script, `gmsh geom.geo -2 -o ...`)
+// SVG outlines (mesher.rs:26-244) are read by the Python mirror only (magnetite_b200/geometry.py).
 #pragma once
 #include <string>
 #include <utility>
@@ -40,6 +43,16 @@ void apply_boundary_conditions(const Json &input_json, std::vector<Node> &nodes,
 void parse_mesh(const std::string &mesh_file, std::vector<Node> &nodes, std::vector<Element> &elements);
 // `areas[e]` = signed area of element e (solver::compute_element_area on the GPU, batched)
 void check_ccw(std::vector<Element> &elements, const std::vector<double> &areas);
+std::vector<Vertex> parse_csv(const std::string &csv_file);
+// container 0 is the outer loop, the others are holes
+std::string geo_text(const std::vector<std::vector<Vertex>> &vertices_containers, float characteristic_length_min,
+                     float characteristic_length_max);
+void build_geo(const std::vector<std::vector<Vertex>> &vertices_containers, const std::string &output_file,
+               float characteristic_length_min, float characteristic_length_max);
+// writes geom.geo, runs `gmsh geom.geo -2 -o <output>`, removes geom.geo; throws Mesher("Gmsh failed: ...") only
+// when gmsh cannot be started, like the reference
+void compute_mesh(const std::vector<std::vector<Vertex>> &vertices, const std::string &output,
+                  float characteristic_length_min, float characteristic_length_max, bool quiet = false);
 }  // namespace mesher
 
 namespace solver {

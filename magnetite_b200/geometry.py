@@ -8,6 +8,9 @@
                      characteristic length, hexagonal interior lattice, scipy Delaunay, triangles
                      whose centroid falls outside OUTER or inside an INNER removed.
 
+    build_geo        src/mesher.rs:305-472   outlines -> the .geo script gmsh meshes (same text as the reference writes)
+    compute_mesh     src/mesher.rs:481-519   build_geo + `gmsh geom.geo -2 -o <msh>` — used when a gmsh binary exists
+
 The stand-in does not reproduce gmsh's node placement (element counts differ from the author's
 runs); it reproduces what the solver sees: 0-based node ids in file order, node defaults
 ux=uy=None / fx=fy=Some(0.0), `check_ccw`, then the boundary rules.  A real `geom.msh` written by
@@ -16,6 +19,8 @@ gmsh is consumed as-is by `parse_mesh`.
 from __future__ import annotations
 
 import math
+import os
+import subprocess
 import xml.etree.ElementTree as ET
 from typing import List, Sequence, Tuple
 
@@ -23,6 +28,92 @@ import numpy as np
 
 from .datatypes import Element, Node, Vertex
 from .error import MagnetiteError
+
+
+# ---------------------------------------------------------------------------
+# outlines -> gmsh (only when a gmsh binary is installed; the stand-in mesher below needs none)
+# ---------------------------------------------------------------------------
+def _rust_display(v, dtype) -> str:
+    """Rust's `{}` for f64 / f32: shortest digits that round-trip IN THAT TYPE, positional, no ".0"."""
+    v = dtype(v)
+    if np.isnan(v):
+        return "NaN"
+    if np.isinf(v):
+        return "inf" if v > 0 else "-inf"
+    return np.format_float_positional(v, unique=True, trim="-")
+
+
+def geo_text(vertices_containers: Sequence[Sequence[Vertex]], characteristic_length_min: float,
+             characteristic_length_max: float) -> str:
+    """The .geo script of build_geo (mesher.rs:305-472), character for character: container 0 is the outer
+    loop, the others are holes; points, lines and loops are numbered per container with running offsets;
+    with exactly two containers the surface lists the loops in reverse (mesher.rs:424-430).  Coordinates
+    print as f64, the characteristic lengths as f32 (ModelMetadata, datatypes.rs:27-28)."""
+    if not vertices_containers:
+        raise MagnetiteError.Input("no geometry was given")          # the reference indexes [0] and panics
+    f = lambda v: _rust_display(v, np.float64)                       # noqa: E731
+    out = ["// Define outer points\n"]
+    for i, v in enumerate(vertices_containers[0]):
+        out.append(f"Point({i}) = {{ {f(v.x)}, {f(v.y)}, 0, 1.0 }};\n")
+    out.append("\n// Define inner points\n")
+    offset = len(vertices_containers[0])
+    inner_offsets = [0]
+    for verts in vertices_containers[1:]:
+        inner_offsets.append(offset)
+        for i, v in enumerate(verts):
+            out.append(f"Point({i + offset}) = {{ {f(v.x)}, {f(v.y)}, 0, 1.0 }};\n")
+        offset += len(verts)
+    out.append("\n// Connect points\n")
+    for i, verts in enumerate(vertices_containers):
+        out.append(f"\n// Point connections for surface {i}\n")
+        off = inner_offsets[i]
+        for k in range(1, len(verts)):
+            out.append(f"Line({k + off - 1}) = {{ {k + off - 1}, {k + off} }};\n")
+        out.append(f"Line({len(verts) + off - 1}) = {{ {len(verts) + off - 1}, {off} }};\n")
+    out.append("\n//Register loops\n")
+    for i, verts in enumerate(vertices_containers):
+        off = inner_offsets[i]
+        out.append(f"Line Loop({i + 1}) = {{")
+        out.extend(f"{',' if k else ''} {k + off}" for k in range(len(verts)))
+        out.append(" };\n")
+    out.append("\n//Define surface\n")
+    out.append("Plane Surface(1) = {")
+    n = len(vertices_containers)
+    order = list(range(n)) if n > 2 else list(reversed(range(n)))
+    out.extend(f"{',' if k else ''} {loop + 1}" for k, loop in enumerate(order))
+    out.append(" };\n")
+    g = lambda v: _rust_display(v, np.float32)                       # noqa: E731
+    out.append("\n// Define Mesh Settings\nMesh.ElementOrder = 1;\nMesh.Algorithm  = 1;\n"
+               f"Mesh.CharacteristicLengthMin = {g(characteristic_length_min)};\n"
+               f"Mesh.CharacteristicLengthMax = {g(characteristic_length_max)};\nMesh 2;\n")
+    return "".join(out)
+
+
+def build_geo(vertices_containers: Sequence[Sequence[Vertex]], output_file: str, characteristic_length_min: float,
+              characteristic_length_max: float) -> None:
+    """mesher.rs:305-472."""
+    text = geo_text(vertices_containers, characteristic_length_min, characteristic_length_max)
+    with open(output_file, "w", newline="") as fh:
+        fh.write(text)
+
+
+def compute_mesh(vertices: Sequence[Sequence[Vertex]], output: str, characteristic_length_min: float,
+                 characteristic_length_max: float, quiet: bool = False) -> None:
+    """mesher.rs:481-519: writes geom.geo, runs `gmsh geom.geo -2 -o <output>`, deletes geom.geo.  Like the
+    reference it only fails when gmsh cannot be started ("Gmsh failed: ..."), not on gmsh's exit status — a
+    failed meshing run surfaces in parse_mesh as "Unable to open auto-generated mesh file"."""
+    geo_filepath = "geom.geo"
+    if not quiet:
+        print("info: building .geo for Gmsh with {:.3f}< CL < {:.3f}".format(
+            float(np.float32(characteristic_length_min)), float(np.float32(characteristic_length_max))))
+    build_geo(vertices, geo_filepath, characteristic_length_min, characteristic_length_max)
+    if not quiet:
+        print("info: running gmsh...")
+    try:
+        subprocess.run(["gmsh", geo_filepath, "-2", "-o", output], capture_output=True)
+    except OSError as err:
+        raise MagnetiteError.Mesher(f"Gmsh failed: {err.strerror} (os error {err.errno})")
+    os.remove(geo_filepath)
 
 
 # ---------------------------------------------------------------------------

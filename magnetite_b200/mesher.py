@@ -1,11 +1,13 @@
 """Input semantics of the reference's mesher that the solver path depends on
-(SURVEY §8(f) rank 1).  The geometry -> gmsh -> .msh part of src/mesher.rs is out of scope;
-these are the pieces that turn a mesh + input.json into the solver's inputs:
+(SURVEY §8(f) rank 1): the pieces that turn a mesh + input.json into the solver's inputs, and the
+entry point that strings the whole input side together.
 
     check_ccw                   src/mesher.rs:522-526  (flips when signed area < 1.0 — sic)
     load_input_file             src/mesher.rs:713-760
     parse_input_metadata        src/mesher.rs:769-808
     apply_boundary_conditions   src/mesher.rs:815-930  (strict > / <, later rules overwrite)
+    run                         src/mesher.rs:939-974  geometry files + input.json -> nodes, elements, metadata
+                                (outline parsing, .geo and the gmsh call live in geometry.py)
 """
 from __future__ import annotations
 
@@ -126,3 +128,34 @@ def check_ccw(elements: Sequence[Element], nodes: Sequence[Node]) -> None:
     for el, a in zip(elements, areas):
         if a < 1.0:
             el.nodes = list(reversed(el.nodes))
+
+
+def run(geometry_files: Sequence[str], input_file: str, quiet: bool = False):
+    """mesher::run (mesher.rs:939-974): (nodes, elements, model_metadata) ready for solver.run.
+
+    An .svg ends the list (its containers replace whatever was read before, mesher.rs:948-950), every .csv
+    adds one container, anything else is an Input error.  The mesh comes from gmsh through geom.geo /
+    geom.msh in the working directory, both removed afterwards like the reference does; check_ccw runs on
+    the GPU (one launch for all elements) before the boundary rules are applied."""
+    import os
+    from . import geometry
+    input_json = load_input_file(input_file)
+    meta = parse_input_metadata(input_json)
+    vertices: list = []
+    for geom in geometry_files:
+        if geom.endswith(".svg"):
+            vertices = geometry.parse_svg(geom, meta.characteristic_length_min)
+            break
+        elif geom.endswith(".csv"):
+            vertices.append(geometry.parse_csv(geom))
+        else:
+            raise MagnetiteError.Input(f"Unrecognized geometry filetype {geom}")
+    mesh_filepath = "geom.msh"
+    geometry.compute_mesh(vertices, mesh_filepath, meta.characteristic_length_min, meta.characteristic_length_max, quiet)
+    nodes, elements = geometry.parse_mesh(mesh_filepath)
+    check_ccw(elements, nodes)                                       # mesher.rs:691-693
+    if not quiet:
+        print(f"info: loaded {len(nodes)} nodes and {len(elements)} elements")   # mesher.rs:695-699
+    os.remove(mesh_filepath)                                         # mesher.rs:701
+    apply_boundary_conditions(input_json, nodes, quiet)
+    return nodes, elements, meta
