@@ -4,11 +4,11 @@
 //                                                      -> nodes.csv, elements.csv in the working directory
 //   magnetite_b200 input.json geom.msh --reorder       the same with the nodes renumbered (reverse Cuthill-McKee)
 //                                                      around the solve; the CSVs keep the mesh file's numbering
-//   magnetite_b200 input.json outline.csv [holes.csv ...]   the reference's own form (main.rs:21-40): CSV outlines
-//                                                      -> geom.geo -> `gmsh geom.geo -2 -o geom.msh` -> the same flow;
-//                                                      needs a gmsh binary on PATH (SVG outlines: Python mirror)
-//   magnetite_b200 --geo out.geo input.json outline.csv [holes.csv ...]   write the gmsh script only (no GPU, no gmsh)
-//   magnetite_b200 --mesh out.msh input.json outline.csv [holes.csv ...]  run gmsh on it and keep the mesh (no GPU)
+//   magnetite_b200 input.json outline.svg | outer.csv [holes.csv ...]   the reference's own form (main.rs:21-40):
+//                                                      outlines -> geom.geo -> `gmsh geom.geo -2 -o geom.msh` -> the
+//                                                      same flow; needs a gmsh binary on PATH
+//   magnetite_b200 --geo out.geo input.json outline.svg|csv...            write the gmsh script only (no GPU, no gmsh)
+//   magnetite_b200 --mesh out.msh input.json outline.svg|csv...           run gmsh on it and keep the mesh (no GPU)
 //   magnetite_b200 --dump-rules input.json             print the parsed metadata and boundary rules (no GPU)
 //   magnetite_b200 --band geom.msh                     node band of the mesh as numbered and after RCM (no GPU)
 //
@@ -64,26 +64,29 @@ int main(int argc, char **argv) {
             const size_t n = std::strlen(suffix);
             return t.size() >= n && t.compare(t.size() - n, n, suffix) == 0;
         };
-        // mesher.rs:946-959: every .csv adds one container (the first is the outer loop); anything else is an error
-        auto read_outlines = [&](int first, int last) {
+        // mesher.rs:946-959: an .svg replaces whatever was read and ends the list, every .csv adds one container
+        // (the first is the outer loop), anything else is an error
+        auto read_outlines = [&](int first, int last, float cl_min) {
             std::vector<std::vector<Vertex>> containers;
             for (int i = first; i < last; ++i) {
                 const std::string geom = argv[i];
                 if (geom.rfind("--", 0) == 0) continue;
-                if (ends_with(geom, ".csv")) containers.push_back(mesher::parse_csv(geom));
-                else throw MagnetiteError(MagnetiteError::Kind::Input, "Unrecognized geometry filetype " + geom +
-                                          (ends_with(geom, ".svg") ? " (SVG outlines are read by the Python mirror)" : ""));
+                if (ends_with(geom, ".svg")) { containers = mesher::parse_svg(geom, cl_min); break; }
+                else if (ends_with(geom, ".csv")) containers.push_back(mesher::parse_csv(geom));
+                else throw MagnetiteError(MagnetiteError::Kind::Input, "Unrecognized geometry filetype " + geom);
             }
             return containers;
         };
         if (argc >= 5 && !std::strcmp(argv[1], "--geo")) {
             const ModelMetadata md = mesher::parse_input_metadata(mesher::load_input_file(argv[3]));
-            mesher::build_geo(read_outlines(4, argc), argv[2], md.characteristic_length_min, md.characteristic_length_max);
+            mesher::build_geo(read_outlines(4, argc, md.characteristic_length_min), argv[2], md.characteristic_length_min,
+                              md.characteristic_length_max);
             return 0;
         }
         if (argc >= 5 && !std::strcmp(argv[1], "--mesh")) {                      // outlines -> gmsh -> out.msh, nothing else
             const ModelMetadata md = mesher::parse_input_metadata(mesher::load_input_file(argv[3]));
-            mesher::compute_mesh(read_outlines(4, argc), argv[2], md.characteristic_length_min, md.characteristic_length_max);
+            mesher::compute_mesh(read_outlines(4, argc, md.characteristic_length_min), argv[2], md.characteristic_length_min,
+                                 md.characteristic_length_max);
             std::vector<Node> nodes;
             std::vector<Element> elements;
             mesher::parse_mesh(argv[2], nodes, elements);
@@ -103,7 +106,7 @@ int main(int argc, char **argv) {
         const ModelMetadata md = mesher::parse_input_metadata(j);
         const bool from_outlines = !ends_with(mesh_file, ".msh");
         if (from_outlines) {                                                     // mesher.rs:946-967
-            const std::vector<std::vector<Vertex>> containers = read_outlines(2, argc);
+            const std::vector<std::vector<Vertex>> containers = read_outlines(2, argc, md.characteristic_length_min);
             mesh_file = "geom.msh";
             mesher::compute_mesh(containers, mesh_file, md.characteristic_length_min, md.characteristic_length_max);
         }

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cctype>
 #include <cerrno>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -310,6 +311,194 @@ std::vector<Vertex> parse_csv(const std::string &csv_file) {              // mes
         vertices.push_back(Vertex{vals[xi], vals[yi]});
     }
     return vertices;
+}
+
+namespace {
+
+// Just enough XML for SVG outlines: elements in document order with their attributes and parent.  Prolog,
+// comments, DOCTYPE, CDATA and text are skipped; attribute values get the XML normalisation (tab / newline ->
+// space) and the five predefined entities plus numeric character references.
+struct XmlNode {
+    std::string name;                                          // local name (prefix stripped)
+    std::vector<std::pair<std::string, std::string>> attrs;
+    int parent = -1;
+    const std::string *attr(const char *key) const {
+        for (const auto &kv : attrs) if (kv.first == key) return &kv.second;
+        return nullptr;
+    }
+};
+
+[[noreturn]] void xml_fail(const std::string &what) {
+    throw MagnetiteError(MagnetiteError::Kind::Input, "Error in svg file: " + what);      // the reference unwrap()s the parser
+}
+
+std::string xml_unescape(const std::string &raw) {
+    std::string out;
+    for (size_t i = 0; i < raw.size(); ++i) {
+        const char c = raw[i];
+        if (c == '\t' || c == '\n' || c == '\r') { out += ' '; continue; }
+        if (c != '&') { out += c; continue; }
+        const size_t semi = raw.find(';', i);
+        if (semi == std::string::npos) xml_fail("unterminated entity");
+        const std::string ent = raw.substr(i + 1, semi - i - 1);
+        if (ent == "amp") out += '&';
+        else if (ent == "lt") out += '<';
+        else if (ent == "gt") out += '>';
+        else if (ent == "quot") out += '"';
+        else if (ent == "apos") out += '\'';
+        else if (ent.size() > 1 && ent[0] == '#') {
+            const long code = (ent[1] == 'x' || ent[1] == 'X') ? std::strtol(ent.c_str() + 2, nullptr, 16)
+                                                               : std::strtol(ent.c_str() + 1, nullptr, 10);
+            if (code <= 0 || code > 0x7f) out += '?'; else out += (char)code;      // ids and numbers are ASCII
+        } else xml_fail("unknown entity &" + ent + ";");
+        i = semi;
+    }
+    return out;
+}
+
+std::vector<XmlNode> parse_xml(const std::string &t) {
+    std::vector<XmlNode> nodes;
+    std::vector<int> open;
+    auto is_space = [](char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; };
+    size_t i = 0;
+    while (i < t.size()) {
+        if (t[i] != '<') { ++i; continue; }                                        // text
+        if (t.compare(i, 4, "<!--") == 0) {
+            const size_t e = t.find("-->", i + 4);
+            if (e == std::string::npos) xml_fail("unterminated comment");
+            i = e + 3;
+        } else if (t.compare(i, 9, "<![CDATA[") == 0) {
+            const size_t e = t.find("]]>", i + 9);
+            if (e == std::string::npos) xml_fail("unterminated CDATA section");
+            i = e + 3;
+        } else if (t.compare(i, 2, "<?") == 0) {
+            const size_t e = t.find("?>", i + 2);
+            if (e == std::string::npos) xml_fail("unterminated processing instruction");
+            i = e + 2;
+        } else if (t.compare(i, 2, "<!") == 0) {                                   // DOCTYPE, possibly with an internal subset
+            int depth = 0;
+            size_t e = i + 2;
+            for (; e < t.size(); ++e) {
+                if (t[e] == '[') ++depth;
+                else if (t[e] == ']') --depth;
+                else if (t[e] == '>' && depth <= 0) break;
+            }
+            if (e >= t.size()) xml_fail("unterminated declaration");
+            i = e + 1;
+        } else if (t.compare(i, 2, "</") == 0) {
+            const size_t e = t.find('>', i + 2);
+            if (e == std::string::npos || open.empty()) xml_fail("unbalanced end tag");
+            open.pop_back();
+            i = e + 1;
+        } else {
+            size_t p = i + 1;
+            const size_t name_start = p;
+            while (p < t.size() && !is_space(t[p]) && t[p] != '>' && t[p] != '/') ++p;
+            if (p == name_start) xml_fail("empty tag name");
+            XmlNode node;
+            node.name = t.substr(name_start, p - name_start);
+            const size_t colon = node.name.rfind(':');
+            if (colon != std::string::npos) node.name.erase(0, colon + 1);
+            node.parent = open.empty() ? -1 : open.back();
+            bool self_closing = false;
+            for (;;) {
+                while (p < t.size() && is_space(t[p])) ++p;
+                if (p >= t.size()) xml_fail("unterminated start tag");
+                if (t[p] == '>') { ++p; break; }
+                if (t[p] == '/') {
+                    if (p + 1 >= t.size() || t[p + 1] != '>') xml_fail("stray '/' in a tag");
+                    self_closing = true;
+                    p += 2;
+                    break;
+                }
+                const size_t key_start = p;
+                while (p < t.size() && !is_space(t[p]) && t[p] != '=' && t[p] != '>' && t[p] != '/') ++p;
+                const std::string key = t.substr(key_start, p - key_start);
+                while (p < t.size() && is_space(t[p])) ++p;
+                if (p >= t.size() || t[p] != '=') xml_fail("attribute " + key + " has no value");
+                ++p;
+                while (p < t.size() && is_space(t[p])) ++p;
+                if (p >= t.size() || (t[p] != '"' && t[p] != '\'')) xml_fail("attribute " + key + " is not quoted");
+                const char quote = t[p++];
+                const size_t end = t.find(quote, p);
+                if (end == std::string::npos) xml_fail("unterminated value of attribute " + key);
+                node.attrs.emplace_back(key, xml_unescape(t.substr(p, end - p)));
+                p = end + 1;
+            }
+            nodes.push_back(std::move(node));
+            if (!self_closing) open.push_back((int)nodes.size() - 1);
+            i = p;
+        }
+    }
+    if (!open.empty()) xml_fail("unclosed element <" + nodes[open.back()].name + ">");
+    return nodes;
+}
+
+double svg_number(const std::string &text) {
+    char *end = nullptr;
+    const double v = std::strtod(text.c_str(), &end);
+    if (text.empty() || end != text.c_str() + text.size())                        // the reference panics (expect)
+        throw MagnetiteError(MagnetiteError::Kind::Input, "Non-float value in svg points");
+    return v;
+}
+
+}  // namespace
+
+std::vector<std::vector<Vertex>> parse_svg(const std::string &svg_file, float min_element_length) {   // mesher.rs:26-244
+    std::ifstream in(svg_file, std::ios::binary);
+    if (!in) throw MagnetiteError(MagnetiteError::Kind::Input, "Unable to open svg file " + svg_file);
+    std::stringstream ss;
+    ss << in.rdbuf();
+    const std::vector<XmlNode> nodes = parse_xml(ss.str());
+    std::vector<std::vector<Vertex>> containers(1);                               // [0]: placeholder for OUTER
+    auto trim_left = [](const std::string &t) {
+        const size_t a = t.find_first_not_of(" \t\r\n");
+        return a == std::string::npos ? std::string() : t.substr(a);
+    };
+    auto file_under = [&](const XmlNode &el, std::vector<Vertex> pts) {            // mesher.rs:97-128, 213-236
+        const std::string *id = el.attr("id");
+        if (!id && el.parent >= 0) id = nodes[(size_t)el.parent].attr("id");
+        if (!id) throw MagnetiteError(MagnetiteError::Kind::Input, "Error in svg file. Missing id field on polyline");
+        const std::string t = trim_left(*id);
+        if (t.rfind("INNER", 0) == 0) containers.push_back(std::move(pts));
+        else if (t.rfind("OUTER", 0) == 0) {
+            if (!containers[0].empty()) throw MagnetiteError(MagnetiteError::Kind::Input, "Multiple OUTER geometries in SVG");
+            containers[0] = std::move(pts);
+        }                                                                          // other ids: the reference warns and skips
+    };
+    for (const XmlNode &el : nodes) {
+        if (el.name != "polyline" && el.name != "polygon") continue;
+        const std::string *raw = el.attr("points");
+        if (!raw) throw MagnetiteError(MagnetiteError::Kind::Input, "Error in svg file. No points in polyline element");
+        std::vector<double> flat;
+        for (size_t a = 0; a <= raw->size();) {
+            const size_t b = raw->find(' ', a);
+            const std::string piece = raw->substr(a, b == std::string::npos ? std::string::npos : b - a);
+            if (!piece.empty()) flat.push_back(svg_number(piece));
+            if (b == std::string::npos) break;
+            a = b + 1;
+        }
+        std::vector<Vertex> pts;
+        for (size_t i = 0; i + 1 < flat.size(); i += 2) {
+            const Vertex v{flat[i], -flat[i + 1]};                                 // mesher.rs:73: y inverted
+            bool seen = false;
+            for (const Vertex &p : pts) if (p.x == v.x && p.y == v.y) { seen = true; break; }
+            if (seen) continue;
+            if (!pts.empty() && std::hypot(pts.back().x - v.x, pts.back().y - v.y) < (double)min_element_length) continue;
+            pts.push_back(v);
+        }
+        file_under(el, std::move(pts));
+    }
+    for (const XmlNode &el : nodes) {
+        if (el.name != "rect") continue;
+        const double x = el.attr("x") ? svg_number(*el.attr("x")) : 0.0, y = el.attr("y") ? svg_number(*el.attr("y")) : 0.0;
+        if (!el.attr("width") || !el.attr("height"))
+            throw MagnetiteError(MagnetiteError::Kind::Input, "Error in svg file. No width/height definition in rectangle.");
+        const double w = svg_number(*el.attr("width")), h = svg_number(*el.attr("height"));
+        file_under(el, {Vertex{x, -y}, Vertex{x + w, -y}, Vertex{x + w, -y - h}, Vertex{x, -y - h}});
+    }
+    if (containers[0].empty()) throw MagnetiteError(MagnetiteError::Kind::Input, "No OUTER geometry");
+    return containers;
 }
 
 std::string geo_text(const std::vector<std::vector<Vertex>> &vc, float cl_min, float cl_max) {   // mesher.rs:305-472

@@ -7,7 +7,7 @@
 //   mesher::check_ccw                                <- src/mesher.rs:522-526 (flips when area < 1.0)
 //   mesher::parse_csv                                <- src/mesher.rs:253-299 (outline vertices, x / y columns)
 //   mesher::geo_text / build_geo / compute_mesh      <- src/mesher.rs:305-519 (.geo script, `gmsh geom.geo -2 -o ...`)
-// SVG outlines (mesher.rs:26-244) are read by the Python mirror only (magnetite_b200/geometry.py).
+//   mesher::parse_svg                                <- src/mesher.rs:26-244  (polygon / polyline / rect with OUTER / INNER* ids)
 #pragma once
 #include <string>
 #include <utility>
@@ -44,6 +44,10 @@ void parse_mesh(const std::string &mesh_file, std::vector<Node> &nodes, std::vec
 // `areas[e]` = signed area of element e (solver::compute_element_area on the GPU, batched)
 void check_ccw(std::vector<Element> &elements, const std::vector<double> &areas);
 std::vector<Vertex> parse_csv(const std::string &csv_file);
+// containers[0] = the OUTER outline, containers[1..] = INNER outlines in document order (polygons and polylines
+// first, then rectangles); y is inverted, repeated vertices and vertices closer than min_element_length to the
+// previous one are dropped
+std::vector<std::vector<Vertex>> parse_svg(const std::string &svg_file, float min_element_length);
 // container 0 is the outer loop, the others are holes
 std::string geo_text(const std::vector<std::vector<Vertex>> &vertices_containers, float characteristic_length_min,
                      float characteristic_length_max);

@@ -1,5 +1,6 @@
 """CPU: geometry input semantics of the reference's mesher (parse_csv, parse_svg, MSH-4 reader) and the
 gmsh-free stand-in mesher; the BASELINE config-1/2 fixtures stay reproducible by the oracle."""
+import re
 from pathlib import Path
 
 import numpy as np
@@ -326,3 +327,62 @@ def test_python_entry_point_follows_main_rs(tmp_path, monkeypatch, capsys):
     assert capsys.readouterr().err.strip() == "Received error: Input error: Unrecognized geometry filetype outline.dxf"
     assert cli.main(["nope.json", "outer.csv"]) == 1
     assert capsys.readouterr().err.strip() == "Received error: Input error: Unable to open input file nope.json"
+
+
+SVG_TRICKY = """<?xml version='1.0' encoding="UTF-8"?>
+<!DOCTYPE svg PUBLIC "-//W3C//DTD SVG 1.1//EN" "http://www.w3.org/Graphics/SVG/1.1/DTD/svg11.dtd" [ <!ENTITY unused "x"> ]>
+<!-- a comment with a <polygon id="OUTER" points="0 0 1 1 2 2"/> inside must not count -->
+<svg:svg xmlns:svg="http://www.w3.org/2000/svg" viewBox="0 0 200 100">
+  <svg:defs><svg:style><![CDATA[ .a > .b { fill: #fff; } <rect id="OUTER" width="1" height="1"/> ]]></svg:style></svg:defs>
+  <svg:g id=' OUTER&#45;shell'>
+    <svg:polygon class="a &amp; b"
+        points='0 0 200 0
+ 200 100 200.2 100 0 100 0 0'/>
+  </svg:g>
+  <svg:polyline id="INNER&#x2d;1" points="20 20  40 20 40 40 20 40"/>
+  <svg:g id="INNER-2"><svg:rect width="10" height="12.5"/></svg:g>
+  <svg:rect id="note" x="1" y="1" width="2" height="2"/>
+  <svg:polygon id = "INNER-3" points="100 50 120 50 110 70"></svg:polygon>
+</svg:svg>
+"""
+
+
+def test_cpp_parse_svg_agrees_with_the_python_mirror(tmp_path, monkeypatch):
+    """host/magnetite_io.cpp parse_svg (own small XML reader) against magnetite_b200.geometry.parse_svg
+    (ElementTree), through the .geo script both write: the repo's test SVG, a deliberately awkward document, and
+    every rejection of mesher.rs:26-244."""
+    import subprocess
+    subprocess.run(["make", "-C", str(ROOT / "host")], check=True, capture_output=True)
+    exe = str(ROOT / "host" / "magnetite_b200")
+    monkeypatch.chdir(tmp_path)
+    inp = tmp_path / "input.json"
+    for k, (text, cl_min) in enumerate(((SVG, 0.5), (SVG, 0.0), (SVG_TRICKY, 0.5), (SVG_TRICKY, 0.0))):
+        (tmp_path / f"g{k}.svg").write_text(text)
+        inp.write_text((GOLDEN / "tensile_input.json").read_text().replace('"characteristic_length_min": 0', f'"characteristic_length_min": {cl_min}'))
+        containers = geometry.parse_svg(f"g{k}.svg", cl_min)
+        r = subprocess.run([exe, "--geo", f"g{k}.geo", "input.json", "ignored.csv", f"g{k}.svg", "never-read.dxf"], capture_output=True, text=True)
+        assert r.returncode == 1 and "Unable to open csv file ignored.csv" in r.stderr         # files before the .svg are still read
+        r = subprocess.run([exe, "--geo", f"g{k}.geo", "input.json", f"g{k}.svg", "never-read.dxf"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr                                                     # the .svg ends the list (mesher.rs:948-950)
+        assert (tmp_path / f"g{k}.geo").read_text() == geometry.geo_text(containers, cl_min, float(np.float32(0.3)))
+    tricky = geometry.parse_svg("g3.svg", 0.0)
+    assert [len(c) for c in tricky] == [5, 4, 3, 4]              # OUTER (closing repeat dropped), polyline, polygon, then the rect
+    assert len(geometry.parse_svg("g2.svg", 0.5)[0]) == 4       # the vertex 0.2 away from its predecessor is skipped at CL 0.5
+    head = '<svg xmlns="http://www.w3.org/2000/svg">'
+    bad = {
+        "no_outer": (head + '<polygon id="INNER" points="0 0 1 0 1 1"/></svg>', "No OUTER geometry"),
+        "two_outer": (head + '<rect id="OUTER" width="5" height="5"/><polygon id="OUTER-2" points="0 0 1 0 1 1"/></svg>', "Multiple OUTER geometries in SVG"),
+        "no_id": (head + '<polygon points="0 0 1 0 1 1"/></svg>', "Error in svg file. Missing id field on polyline"),
+        "no_points": (head + '<polygon id="OUTER"/></svg>', "Error in svg file. No points in polyline element"),
+        "no_width": (head + '<rect id="OUTER" height="5"/></svg>', "Error in svg file. No width/height definition in rectangle."),
+        "not_float": (head + '<polygon id="OUTER" points="0 0 1 zero 1 1"/></svg>', "Non-float value in svg points"),
+    }
+    inp.write_text((GOLDEN / "tensile_input.json").read_text())
+    for name, (text, msg) in bad.items():
+        (tmp_path / f"{name}.svg").write_text(text)
+        with pytest.raises(MagnetiteError, match=re.escape(msg)):
+            geometry.parse_svg(f"{name}.svg", 0.0)
+        r = subprocess.run([exe, "--geo", "e.geo", "input.json", f"{name}.svg"], capture_output=True, text=True)
+        assert r.returncode == 1 and r.stderr.strip().startswith(f"Received error: Input error: {msg}"), (name, r.stderr)
+    r = subprocess.run([exe, "--geo", "e.geo", "input.json", "absent.svg"], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stderr.strip() == "Received error: Input error: Unable to open svg file absent.svg"
