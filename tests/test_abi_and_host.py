@@ -206,8 +206,10 @@ def test_cpp_cli_parses_input_json_like_the_python_mirror(built):
         want.append(f"rule {rule.name} region {f(g.x_min)} {f(g.x_max)} {f(g.y_min)} {f(g.y_max)} "
                     f"targets {o(tg.ux)} {o(tg.uy)} {o(tg.fx)} {o(tg.fy)}")
     assert r.stdout.splitlines() == want
-    bad = subprocess.run([str(ROOT / "host" / "magnetite_b200"), path, "outline.svg"], capture_output=True, text=True)
-    assert bad.returncode == 1 and "Received error: Input error: Unrecognized geometry filetype" in bad.stderr
+    bad = subprocess.run([str(ROOT / "host" / "magnetite_b200"), path, "outline.dxf"], capture_output=True, text=True)
+    assert bad.returncode == 1 and bad.stderr.strip() == "Received error: Input error: Unrecognized geometry filetype outline.dxf"
+    bad = subprocess.run([str(ROOT / "host" / "magnetite_b200"), path, "absent.svg"], capture_output=True, text=True)
+    assert bad.returncode == 1 and bad.stderr.strip() == "Received error: Input error: Unable to open svg file absent.svg"
 
 
 def test_library_csv_writer_matches_python_writer(tmp_path, built):
