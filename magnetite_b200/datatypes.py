@@ -106,20 +106,17 @@ class MeshSoA:
     @staticmethod
     def from_aos(nodes: Sequence[Node], elements: Sequence[Element]) -> "MeshSoA":
         n, e = len(nodes), len(elements)
-        x = np.empty(n); y = np.empty(n)
-        ux = np.zeros(n); uy = np.zeros(n); fx = np.zeros(n); fy = np.zeros(n)
+        x = np.fromiter((nd.vertex.x for nd in nodes), np.float64, n)
+        y = np.fromiter((nd.vertex.y for nd in nodes), np.float64, n)
         known = np.zeros(n, np.uint8)
-        for i, nd in enumerate(nodes):
-            x[i] = nd.vertex.x; y[i] = nd.vertex.y
-            k = 0
-            if nd.ux is not None: ux[i] = nd.ux; k |= KNOWN_UX
-            if nd.uy is not None: uy[i] = nd.uy; k |= KNOWN_UY
-            if nd.fx is not None: fx[i] = nd.fx; k |= KNOWN_FX
-            if nd.fy is not None: fy[i] = nd.fy; k |= KNOWN_FY
-            known[i] = k
-        conn = np.empty((e, 3), np.int64)
-        for i, el in enumerate(elements):
-            conn[i] = el.nodes
+        payload = []
+        for attr, bit in (("ux", KNOWN_UX), ("uy", KNOWN_UY), ("fx", KNOWN_FX), ("fy", KNOWN_FY)):
+            opt = [getattr(nd, attr) for nd in nodes]                     # Option<f64>: None or a float
+            some = np.fromiter((v is not None for v in opt), np.bool_, n)
+            known |= some.astype(np.uint8) * np.uint8(bit)
+            payload.append(np.fromiter((0.0 if v is None else v for v in opt), np.float64, n))
+        ux, uy, fx, fy = payload
+        conn = (np.array([el.nodes for el in elements], np.int64).reshape(e, 3) if e else np.empty((0, 3), np.int64))
         if e and (conn.min() < 0 or conn.max() >= 2 ** 32):
             raise ValueError("element node index does not fit usize/u32")
         conn = conn.astype(np.uint32)
