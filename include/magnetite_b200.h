@@ -176,6 +176,13 @@ int mag_stress(mag_ctx *ctx, const mag_mesh *mesh, const mag_material *mat, cons
 int mag_system_spmv(mag_system *sys, int format, const double *x, double *y);
 int mag_system_spmv_bench(mag_system *sys, int format, int reps, float *ms_per_spmv,
                           uint64_t *algorithmic_bytes);
+/* True residual of a returned displacement field over the rows this rank owns:
+ * *rr_owned = sum (b - K_ff x)^2, *bb_owned = sum b^2, x rebuilt from (ux, uy) through the free-DOF map, the row
+ * products in the reference's order (src/solver.rs:31-36).  ux, uy: n_nodes each, host (on_device = 0) or device
+ * pointers.  Not collective: a multi-GPU caller adds both sums over the ranks.  The check a caller runs on the
+ * result of solver::run (src/solver.rs:412-487), which only ever sees CG's recursive residual. */
+int mag_system_residual(mag_system *sys, const double *ux, const double *uy, int on_device,
+                        double *rr_owned, double *bb_owned);
 
 /* ---- output stage: post_processor::csv_output (src/post_processor.rs:18-83), host only ---------
  * nodes.csv "x,y,ux,uy", elements.csv "n0,n1,n2,stress", "\n" line ends, f64 printed like Rust's `{}`

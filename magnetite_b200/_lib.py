@@ -98,6 +98,7 @@ _SIGNATURES = {
     "mag_stress": (C.c_int, [_vp, C.POINTER(MagMesh), C.POINTER(MagMaterial), _vp, _vp, _vp, _vp]),
     "mag_system_spmv": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "mag_system_spmv_bench": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
+    "mag_system_residual": (C.c_int, [_vp, _vp, _vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mag_csv_output": (C.c_int, [C.c_char_p, C.c_char_p, C.c_uint64, _vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp, _vp, _vp]),
     "mag_format_f64": (C.c_size_t, [C.c_double, C.c_char_p]),
     "mag_host_last_error": (C.c_char_p, []),

@@ -397,6 +397,45 @@ extern "C" int mag_system_spmv(mag_system *sys, int format, const double *x, dou
     });
 }
 
+// ||b - K_ff x||^2 and ||b||^2 over the rows this rank owns, for the displacement field (ux, uy) a solve
+// returned: x is rebuilt from the nodal values through the column map, the products run through the
+// ordered CSR kernel.  Not collective: a multi-GPU caller adds the two sums over the ranks.
+extern "C" int mag_system_residual(mag_system *sys, const double *ux, const double *uy, int on_device,
+                                   double *rr_owned, double *bb_owned) {
+    return guarded([&] {
+        if (!sys || !rr_owned || !bb_owned || (sys->n_nodes && (!ux || !uy))) fail(MAG_ERR_BAD_ARG, "null argument");
+        mag_ctx *ctx = sys->ctx;
+        CallScope scope(ctx, nullptr);
+        const size_t N = sys->n_nodes, n = sys->Kff.n_rows, nx = sys->n_free;
+        DevBuf<double> dux, duy, dx(ctx, nx + 32);
+        const double *pux = ux, *puy = uy;
+        if (!on_device) {
+            dux.alloc(ctx, N); duy.alloc(ctx, N);
+            copy_to_device(ctx, dux.p, ux, N, false);
+            copy_to_device(ctx, duy.p, uy, N, false);
+            pux = dux.p; puy = duy.p;
+        }
+        dx.zero();
+        if (N)
+            MAG_LAUNCH(ctx, gather_solution_kernel, cdiv(N, 256), 256, 0, (const uint8_t *)sys->known.p,
+                       (const uint32_t *)sys->colmap.p, pux, puy, N, dx.p);
+        const unsigned grid = std::max(1u, std::min(cdiv(n, 256), (unsigned)ctx->sm_count * 8u));
+        DevBuf<double> partials(ctx, 2 * (size_t)grid), out(ctx, 2);
+        DevBuf<unsigned> ticket(ctx, 1);
+        ticket.zero();
+        out.zero();
+        const CsrMatrix &A = sys->Kff;
+        MAG_LAUNCH(ctx, true_residual_kernel, grid, 256, 0, (const uint32_t *)A.rowptr.p, (const int32_t *)A.col.p,
+                   (const double *)A.val.p, (const double *)dx.p, (const double *)sys->rhs.p, A.n_rows, partials.p,
+                   ticket.p, out.p);
+        double h[2] = {0.0, 0.0};
+        MAG_CUDA(cudaMemcpyAsync(h, out.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+        *rr_owned = h[0];
+        *bb_owned = h[1];
+    });
+}
+
 extern "C" int mag_system_spmv_bench(mag_system *sys, int format, int reps, float *ms_per_spmv,
                                      uint64_t *algorithmic_bytes) {
     return guarded([&] {

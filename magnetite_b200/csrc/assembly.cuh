@@ -88,7 +88,9 @@ segment_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restr
     int steps = is_head ? in_warp_len - 1 : 0;
 #pragma unroll 1
     for (int off = 16; off > 0; off >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, off));
-    double a0 = v0, a1 = v1, a2 = v2, a3 = v3;
+    // the reference adds every contribution, the first included, to a zeroed dense entry (solver.rs:295-296,
+    // 304-323): 0.0 + (-0.0) = +0.0, so a lone -0.0 contribution is stored as +0.0
+    double a0 = __dadd_rn(0.0, v0), a1 = __dadd_rn(0.0, v1), a2 = __dadd_rn(0.0, v2), a3 = __dadd_rn(0.0, v3);
     for (int j = 1; j <= steps; ++j) {
         const double t0 = __shfl_down_sync(0xffffffffu, v0, j);
         const double t1 = __shfl_down_sync(0xffffffffu, v1, j);

@@ -24,13 +24,19 @@ __device__ __forceinline__ bool dof_f_known(const uint8_t *known, uint32_t dof) 
     return (known[dof >> 1] >> (2 + (dof & 1))) & 1u;      // MAG_KNOWN_FX=4, FY=8
 }
 
-// rowflag[d] = force known, colflag[d] = displacement unknown.
+// rowflag[d] = force known, colflag[d] = displacement unknown.  *unpaired is set when some DOF has both
+// or neither (the reference's mesher never produces that, mesher.rs:881-900; its solver only compares
+// the two counts, solver.rs:380-396): such a system can be assembled and exported, not solved.
 __global__ void dof_flags_kernel(const uint8_t *__restrict__ known, size_t n_dof,
-                                 uint32_t *__restrict__ rowflag, uint32_t *__restrict__ colflag) {
+                                 uint32_t *__restrict__ rowflag, uint32_t *__restrict__ colflag,
+                                 int *__restrict__ unpaired) {
     const size_t d = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n_dof) return;
-    rowflag[d] = dof_f_known(known, (uint32_t)d) ? 1u : 0u;
-    colflag[d] = dof_u_known(known, (uint32_t)d) ? 0u : 1u;
+    const uint32_t rf = dof_f_known(known, (uint32_t)d) ? 1u : 0u;
+    const uint32_t cf = dof_u_known(known, (uint32_t)d) ? 0u : 1u;
+    rowflag[d] = rf;
+    colflag[d] = cf;
+    if (rf != cf) *unpaired = 1;
 }
 
 // Pass 1 (fill == 0): count kept entries of every owned reduced row.
@@ -101,6 +107,17 @@ __global__ void scatter_solution_kernel(const uint8_t *__restrict__ known,
     const uint8_t k = known[i];
     ux[i] = (k & MAG_KNOWN_UX) ? bc_ux[i] : xsol[colmap[2 * i]];
     uy[i] = (k & MAG_KNOWN_UY) ? bc_uy[i] : xsol[colmap[2 * i + 1]];
+}
+
+// Inverse of the scatter: xsol[colmap[d]] = U[d] for every DOF whose displacement is unknown.
+__global__ void gather_solution_kernel(const uint8_t *__restrict__ known, const uint32_t *__restrict__ colmap,
+                                       const double *__restrict__ ux, const double *__restrict__ uy,
+                                       size_t n_nodes, double *__restrict__ xsol) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const uint8_t k = known[i];
+    if (!(k & MAG_KNOWN_UX)) xsol[colmap[2 * i]] = ux[i];
+    if (!(k & MAG_KNOWN_UY)) xsol[colmap[2 * i + 1]] = uy[i];
 }
 
 // solver.rs:457-473 — forces: prescribed where known, else the full-row product.

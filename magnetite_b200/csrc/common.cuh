@@ -86,6 +86,7 @@ struct mag_ctx {
     mag::DeviceHeap heap;
     uint64_t launches = 0;              // kernels launched by the current call
     int tune = 0;                       // MAG_TUNE debug switches (see PcgScalars::tune)
+    bool rs_attr_set = false;           // radix sort: dynamic shared memory opt-in done on this device
     void *cusolver = nullptr;           // cusolverDnHandle_t, created on first use of the two-level preconditioner
     mag::Comm *comm = nullptr;
     // pinned host scratch for scalar read-backs

@@ -181,8 +181,8 @@ MAG_HD void fill_row(const Conn &m, const Pt *xy, const double *D, double t, con
                 const double v0 = rows[0][2 * lc], v1 = rows[0][2 * lc + 1], v2 = rows[1][2 * lc], v3 = rows[1][2 * lc + 1];
                 if ((seen >> slot) & 1u) {
                     a[0] = gadd(a[0], v0); a[1] = gadd(a[1], v1); a[2] = gadd(a[2], v2); a[3] = gadd(a[3], v3);
-                } else {
-                    a[0] = v0; a[1] = v1; a[2] = v2; a[3] = v3;
+                } else {       // the reference's entry starts at +0.0 (zeroed dense matrix): 0.0 + (-0.0) = +0.0
+                    a[0] = gadd(0.0, v0); a[1] = gadd(0.0, v1); a[2] = gadd(0.0, v2); a[3] = gadd(0.0, v3);
                     seen |= 1u << slot;
                 }
             }
@@ -199,7 +199,6 @@ MAG_HD void fill_row(const Conn &m, const Pt *xy, const double *D, double t, con
     for (uint32_t j = 0; j < ncols && next_col(m, pay, begin, end, have, c, &c); ++j) {
         have = true;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        bool first = true;
         for (uint32_t i = begin; i < end; ++i) {
             const uint32_t p = pay[i], le = p / 3u;
             const int lr = (int)(p - 3u * le);
@@ -211,8 +210,7 @@ MAG_HD void fill_row(const Conn &m, const Pt *xy, const double *D, double t, con
             for (int lc = 0; lc < 3; ++lc) {
                 if (nd[lc] != c) continue;
                 const double v0 = rows[0][2 * lc], v1 = rows[0][2 * lc + 1], v2 = rows[1][2 * lc], v3 = rows[1][2 * lc + 1];
-                if (first) { a0 = v0; a1 = v1; a2 = v2; a3 = v3; first = false; }
-                else { a0 = gadd(a0, v0); a1 = gadd(a1, v1); a2 = gadd(a2, v2); a3 = gadd(a3, v3); }
+                a0 = gadd(a0, v0); a1 = gadd(a1, v1); a2 = gadd(a2, v2); a3 = gadd(a3, v3);   // from +0.0, like the reference
             }
         }
         bcol[j] = c;

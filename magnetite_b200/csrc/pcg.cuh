@@ -46,7 +46,10 @@
 namespace mag {
 
 struct PcgScalars {
-    double pair[2][2];   // pair[parity] = {r.z, r.r} entering an iteration of that parity (global sums)
+    double pair[2][2];   // pair[parity] = {r.Dinv r, r.r} entering an iteration of that parity (global sums)
+    double rzc[2];       // rzc[parity] = complete r.z entering an iteration of that parity: pair[parity][0], plus
+                         // the coarse part wy with the two-level preconditioner.  Written by ONE thread of the
+                         // p-update and read only by LATER launches (never input and output of the same launch).
     double pq;           // global p.q
     double wy;           // two-level preconditioner: (P^T r).(Ac^-1 P^T r), the coarse part of r.z
     double loc_pair[2];  // this rank's partial sums (send buffers of the NCCL fallback)
@@ -266,7 +269,7 @@ pcg_update_xr_kernel(double *__restrict__ x, double *__restrict__ r, const doubl
         if (blockIdx.x == 0 && threadIdx.x == 0) sc->pq = pq;
     }
     const bool do_push = push.n && !(sc->tune & 1);
-    const double alpha = sc->pair[parity][0] / pq;
+    const double alpha = sc->rzc[parity] / pq;
     double v[2] = {0.0, 0.0};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t gi = row_lo + i;
@@ -315,15 +318,16 @@ pcg_update_p_kernel(double *__restrict__ p, const double *__restrict__ r,
         const double2 g = mailbox_gather(links, kMailPair, parity, seq, sc, 6);
         rz_new = g.x; rr = g.y;
     }
+    const double g_rz = rz_new;
     if (cv.mode) rz_new += sc->wy;          // r.z = r.Dinv r + (P^T r).(Ac^-1 P^T r)
-    const double rz_old = sc->pair[parity][0], pq = sc->pq;
+    const double rz_old = sc->rzc[parity], pq = sc->pq;
     const bool use_halo = halo.ll != nullptr && !(sc->tune & 1);
     // One thread moves the iteration on.  Nothing another CTA of this launch still reads is
     // touched: sequence numbers come from chunk_base + step (constant during the launch), and a
     // CTA that starts late and already sees the stop flag just skips an update nobody needs.
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        sc->pair[parity ^ 1][0] = rz_new;
-        sc->pair[parity ^ 1][1] = rr;
+        sc->rzc[parity ^ 1] = rz_new;       // a field of its own: pair[parity^1][0] is still being read by late CTAs
+        if (links.n) { sc->pair[parity ^ 1][0] = g_rz; sc->pair[parity ^ 1][1] = rr; }   // mailbox mode: inputs came from the mailbox
         sc->prof[7] += 1.0;
         const unsigned long long it = sc->iter + 1;
         if (sc->iter == 0) sc->first_pq = pq;
@@ -390,10 +394,13 @@ pcg_init_p_kernel(double *__restrict__ p, const double *__restrict__ r, const do
     const uint32_t seq = ll_seq(sc, 0);
     if (links.n) {
         const double2 g = mailbox_gather(links, kMailInit, 0, seq, sc, -1);
-        if (blockIdx.x == 0 && threadIdx.x == 0) { sc->pair[0][0] = g.x + (cv.mode ? sc->wy : 0.0); sc->pair[0][1] = g.y; }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            sc->pair[0][0] = g.x; sc->pair[0][1] = g.y;
+            sc->rzc[0] = g.x + (cv.mode ? sc->wy : 0.0);
+        }
         __threadfence_system();        // acquire side of the Dinv halo
-    } else if (cv.mode && blockIdx.x == 0 && threadIdx.x == 0) {
-        sc->pair[0][0] += sc->wy;
+    } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->rzc[0] = sc->pair[0][0] + (cv.mode ? sc->wy : 0.0);
     }
     const uint32_t n = ext_hi - ext_lo;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {

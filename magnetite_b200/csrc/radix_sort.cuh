@@ -144,12 +144,11 @@ inline void radix_sort_pairs(mag_ctx *ctx, uint64_t *keys, uint32_t *payload, ui
                              uint32_t *payload_alt, size_t n, int key_bits) {
     if (n < 2 || key_bits <= 0) return;
     if (n > 0xffffffffull) fail(MAG_ERR_BAD_ARG, "radix_sort_pairs: more than 2^32 pairs");
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->rs_attr_set) {      // a per-device attribute: kept per context, not per process
         MAG_CUDA(cudaFuncSetAttribute(rs_scatter_kernel,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kRsSmemBytes));
-        attr_set = true;
+        ctx->rs_attr_set = true;
     }
     const uint32_t n_tiles = cdiv(n, kRsTile);
     const size_t hist_n = (size_t)kRadix * n_tiles;

@@ -417,7 +417,7 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
     for (RankState &W : ranks) {
         PcgScalars init;
         std::memset(&init, 0, sizeof init);
-        init.pair[0][0] = hs.pair[0][0]; init.pair[0][1] = hs.pair[0][1];
+        init.pair[0][0] = hs.pair[0][0]; init.pair[0][1] = hs.pair[0][1]; init.rzc[0] = hs.rzc[0];
         init.thr2 = thr2; init.max_iter = opt.max_iter; init.stop = stop0;
         init.best_rr = bb; init.best_iter = 0;
         init.epoch = W.S->solve_epoch;
@@ -538,6 +538,13 @@ static void post_local(mag_ctx *ctx, mag_system *S, PostBuffers &B, bool want_si
 
 static void check_result_args(const mag_system *S, const mag_result *out) {
     if (!out) fail(MAG_ERR_BAD_ARG, "null result");
+    // The reduced row and column numberings must coincide DOF by DOF: the Jacobi diagonal, the solution
+    // scatter and the row-block halo layout all rely on it.  The counts alone (what the reference compares,
+    // solver.rs:380-396) do not guarantee it.
+    if (!S->bc_paired)
+        fail(MAG_ERR_BAD_BC, "inconsistent boundary conditions: some DOF has both its displacement and its force "
+                             "known, or neither; the solve needs exactly one of the two per DOF "
+                             "(the reference's mesher enforces this, mesher.rs:881-900)");
     if (S->n_nodes && (!out->ux || !out->uy || !out->fx || !out->fy)) fail(MAG_ERR_BAD_ARG, "result: ux, uy, fx, fy are required");
     if (S->n_elems && !out->stress) fail(MAG_ERR_BAD_ARG, "result: stress is required");
 }

@@ -328,6 +328,26 @@ spmv_csr_kernel(const uint32_t *__restrict__ rowptr, const int32_t *__restrict__
     y[row] = acc;
 }
 
+// True residual of the owned rows: out[0] = sum_i (b_i - (K_ff x)_i)^2, out[1] = sum_i b_i^2, with the row
+// products in the reference's order (ascending column, product then sum, no FMA) and a deterministic grid sum.
+__global__ void __launch_bounds__(256)
+true_residual_kernel(const uint32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                     const double *__restrict__ val, const double *__restrict__ x, const double *__restrict__ b,
+                     uint32_t n_rows, double *__restrict__ partials, unsigned *__restrict__ ticket,
+                     double *__restrict__ out) {
+    double v[2] = {0.0, 0.0};
+    for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (uint32_t p = rowptr[row]; p < rowptr[row + 1]; ++p)
+            acc = __dadd_rn(acc, __dmul_rn(val[p], __ldg(x + col[p])));
+        const double bi = b[row], d = bi - acc;
+        v[0] = fma(d, d, v[0]);
+        v[1] = fma(bi, bi, v[1]);
+    }
+    double tot[2] = {0.0, 0.0};
+    if (grid_sum_256<2>(v, partials, ticket, tot)) { out[0] = tot[0]; out[1] = tot[1]; }
+}
+
 inline unsigned sell_grid(const mag_ctx *ctx, uint32_t n_slices) {
     const unsigned need = cdiv(n_slices, 8);
     const unsigned cap = (unsigned)ctx->sm_count * 6u;

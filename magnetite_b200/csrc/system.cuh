@@ -48,6 +48,7 @@ struct mag_system {
     mag::PeerLinks links;                    // peer mailboxes (production multi-rank only)
     unsigned long long solve_epoch = 0;
     bool push_ready = false;
+    bool bc_paired = true;                   // every DOF has exactly one of {displacement, force} known
     std::vector<uint32_t> all_row_lo, all_node_lo;   // nranks+1
     mag_stats stats{};
 
@@ -190,7 +191,8 @@ static void assemble_impl(mag_ctx *ctx, const mag_mesh *m, const mag_material *m
     BsrMatrix &K = S->K;
     K.node_lo = S->node_lo; K.node_hi = S->node_hi;
     const uint32_t n_own = K.node_hi - K.node_lo;
-    const bool use_gather = opt && opt->assembly == 1;
+    const int asm_mode = opt ? opt->assembly : 0;       // 0 default, 1 gather -> BSR -> eliminate, 2 sorted COO keys
+    const bool use_gather = asm_mode == 1;
     if (use_gather) {
         // gather assembly (gather.cuh): no K_e in memory, 3E incidences sorted by node instead of 9E COO keys
         st.ms_elem = phase.stop();                  // only the rank's element list: K_e rows are recomputed in the gather
@@ -252,9 +254,17 @@ static void assemble_impl(mag_ctx *ctx, const mag_mesh *m, const mag_material *m
     phase.start();
     S->rowmap.alloc(ctx, n_dof + 1);
     S->colmap.alloc(ctx, n_dof + 1);
+    DevBuf<int> unpaired(ctx, 1);
+    unpaired.zero();
     if (n_dof)
         MAG_LAUNCH(ctx, dof_flags_kernel, cdiv(n_dof, 256), 256, 0, (const uint8_t *)S->known.p, n_dof,
-                   S->rowmap.p, S->colmap.p);
+                   S->rowmap.p, S->colmap.p, unpaired.p);
+    {
+        int h_unpaired = 0;
+        MAG_CUDA(cudaMemcpyAsync(&h_unpaired, unpaired.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+        S->bc_paired = h_unpaired == 0;
+    }
     exclusive_scan_u32(ctx, S->rowmap.p, n_dof, S->rowmap.p, n_dof + 1);
     exclusive_scan_u32(ctx, S->colmap.p, n_dof, S->colmap.p, n_dof + 1);
     const uint32_t n_rows_glob = read_u32(ctx, S->rowmap.p + n_dof);

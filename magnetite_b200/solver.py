@@ -132,6 +132,14 @@ class System:
         check(load().mag_system_spmv(self._h, fmt, ptr(x), ptr(y)), "mag_system_spmv")
         return y
 
+    def true_residual(self, ux: np.ndarray, uy: np.ndarray):
+        """(sum (b - K_ff x)^2, sum b^2) over the rows this rank owns for a returned displacement field
+        (mag_system_residual: x rebuilt through the free-DOF map, row products in the reference's order)."""
+        ux, uy = np.ascontiguousarray(ux, np.float64), np.ascontiguousarray(uy, np.float64)
+        rr, bb = C.c_double(), C.c_double()
+        check(load().mag_system_residual(self._h, ptr(ux), ptr(uy), 0, C.byref(rr), C.byref(bb)), "mag_system_residual")
+        return float(rr.value), float(bb.value)
+
     def spmv_bench(self, reps: int = 50, fmt: int = 2):
         ms = C.c_float()
         nbytes = C.c_uint64()

@@ -32,11 +32,20 @@ def main():
             err = np.linalg.norm(u - u1) / np.linalg.norm(u1)
             ferr = np.abs(np.concatenate([sol.fx - one.fx, sol.fy - one.fy])).max() / np.abs(one.fx).max()
             serr = np.abs(sol.stress - one.stress).max() / np.abs(one.stress).max()
-            assert 0.1 < sol.stats["final_residual"] / one.stats["final_residual"] < 10.0   # same stopping point
-            print(f"rank0: {mesh.n_elems} elements, world {world}, allreduce {allreduce}, precond {precond}: iters {sol.stats['iters']} vs {one.stats['iters']}, "
-                  f"|du| {err:.2e}, |df| {ferr:.2e}, |ds| {serr:.2e}", flush=True)
+            # both runs stopped on the same criterion (the residual at the stopping iteration is rounding noise at
+            # 1e-12 relative, so its VALUE differs between summation orders; the bound is what must hold)
+            for s in (sol, one):
+                assert s.stats["converged"] == 1 and s.stats["final_residual"] <= 1e-12 * s.stats["b_norm"]
+            # the one-process emulation of the same partition (virtual ranks): same kernels, same summation order
+            emu = solver.virtual_rank_solve(mesh, meta, world, solo, opt)
+            ue = np.concatenate([emu.ux, emu.uy])
+            err_emu = np.linalg.norm(u - ue) / np.linalg.norm(ue)
+            print(f"rank0: {mesh.n_elems} elements, world {world}, allreduce {allreduce}, precond {precond}: iters {sol.stats['iters']} "
+                  f"(1 GPU: {one.stats['iters']}, emulation: {emu.stats['iters']}), |du| {err:.2e}, |df| {ferr:.2e}, |ds| {serr:.2e}, "
+                  f"vs emulation |du| {err_emu:.2e} (bit-identical: {u.tobytes() == ue.tobytes()})", flush=True)
             assert err < 1e-9 and ferr < 1e-7 and serr < 1e-8
-            assert abs(int(sol.stats["iters"]) - int(one.stats["iters"])) <= 5
+            assert abs(int(sol.stats["iters"]) - int(one.stats["iters"])) <= max(5, int(one.stats["iters"]) // 100)
+            assert err_emu < 1e-9 and abs(int(sol.stats["iters"]) - int(emu.stats["iters"])) <= max(5, int(emu.stats["iters"]) // 100)
             solo.close()
     import torch.distributed as dist
     dist.barrier()

@@ -27,11 +27,23 @@ def test_reference_arm_prints_one_contract_line(built):
     assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1
     assert d["unit"] == "Melem/s" and d["higher_is_better"] is True and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert d["vs_baseline"] is None and d["scaling"] in ("weak", "strong") and d["value"] > 0 and d["ms_per_step"] > 0
-    assert "4000x2000" in d["config"]["workload"] and "40x20" in d["config"]["sample"]      # our arm's workload, a bounded sample of it
+    import argparse
+    sys.path.insert(0, str(ROOT))
+    import bench
+    args = argparse.Namespace(workload="c4", nx=4000, ny=2000)
+    assert d["config"] == bench.config_of(args, 1)                     # exactly the GPU arm's config object
+    assert "4000x2000" in d["config"]["workload"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == d["value"] and cb["unit"] == d["unit"] and cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == d["value"] and cb["unit"] == d["unit"]
+    assert "strip 4000x" in cb["sample"] and "17203 iterations" in cb["sample"]             # a bounded sample of that workload
+    det = cb["sample_detail"]
+    est = det["scale_rows"] * (det["seconds_serial_phases"] + det["job_cg_iterations"] * det["seconds_per_cg_iteration"])
+    assert abs(est - det["job_seconds_estimated"]) < 1e-6 * est
+    assert abs(d["value"] - 16e6 / cb["job_seconds_estimated"] / 1e6) < 1e-9 * d["value"]
+    assert d["ms_per_step"] < 60e3 and d["job_ms_estimated"] > d["ms_per_step"]              # the step is the sample, not the job
+    assert cb["complete_small"]["cg_iters"] > 0 and "40x20" in cb["complete_small"]["workload"]
     assert cb["faithful_dense"]["cg_iters"] > 0 and cb["faithful_dense"]["seconds"] > 0
-    ac = cb["all_cores"]                        # extra figure: the same sample with the CG on every host core
+    ac = cb["all_cores"]                        # extra figure: the completely solved plate with the CG on every host core
     assert ac["threads"] >= 1 and ac["value"] > 0 and ac["unit"] == d["unit"] and "not the reference" in ac["note"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0                                                              # nothing of ours ran on a GPU

@@ -279,6 +279,46 @@ def test_full_size_properties_1m_triangles(ctx):
     assert 0.5 < mid / (69e9 * 3.0 / 2000.0) < 1.5            # ~ E * strain in the middle of the plate
 
 
+def test_config3_kff_bit_exact_against_oracle(ctx):
+    """BASELINE configs[2] (1 M triangles, 1000 x 500 cells) at full size: K_ff (pattern and values), rhs and the
+    free-DOF numbering bit for bit against the oracle's assembly + partition (solver.rs:290-404, 126-137) — a few
+    seconds of CPU, no CPU solve — and the TRUE residual of the device solve through mag_system_residual."""
+    mesh = meshgen.plate(1000, 500)
+    om = O.Mesh(mesh)
+    (rp_r, col_r, val_r), rhs_r, fmap_r = O.partition(om, O.assemble_sparse(om, O.element_stiffness(om, META)), dense=False)
+    with solver.System(mesh, META, ctx) as S:
+        rp, col, val, rhs, fmap = S.export_kff()
+        assert np.array_equal(rp, rp_r) and np.array_equal(col, col_r) and np.array_equal(fmap, fmap_r)
+        assert np.array_equal(val.view(np.uint64), val_r.view(np.uint64))            # bit patterns, signed zeros included
+        assert np.array_equal(rhs.view(np.uint64), rhs_r.view(np.uint64))
+        sol = S.solve(_lib.default_options())
+        rr, bb = S.true_residual(sol.ux, sol.uy)
+        assert np.sqrt(rr / bb) <= 2e-9
+        # the oracle's own row sums on the device result agree with the device's residual
+        x = np.where(fmap >= 0, np.stack([sol.ux, sol.uy], 1).ravel(), 0.0)[fmap >= 0]
+        r = rhs_r - O.spmv((rp_r, col_r, val_r), x)
+        assert abs(np.dot(r, r) - rr) <= 1e-9 * rr and abs(np.dot(rhs_r, rhs_r) - bb) <= 1e-12 * bb
+
+
+def test_signed_zero_entries_follow_the_reference(ctx):
+    """The reference adds every contribution to a zeroed dense entry (solver.rs:295-296, 304-323): a lone -0.0
+    contribution is stored as +0.0.  Clockwise triangles produce -0.0 in B (0/den with den < 0): the full K must
+    match the oracle's bit patterns, not just compare equal."""
+    def flipped(m):                       # what check_ccw (mesher.rs:522-526) does when every area is < 1
+        m = m.copy()
+        m.n0, m.n2 = m.n2.copy(), m.n0.copy()
+        return m
+
+    for mesh in (flipped(meshgen.plate(12, 7, h=0.5)), flipped(meshgen.jitter(meshgen.plate(9, 6))), meshgen.plate(9, 6)):
+        om = O.Mesh(mesh)
+        full_ref = O.assemble_sparse(om, O.element_stiffness(om, META))
+        for assembly in (0, 1, 2):
+            with solver.System(mesh, META, ctx, _lib.default_options(assembly=assembly)) as S:
+                rp, col, val = S.export_full()
+            assert np.array_equal(rp, full_ref[0]) and np.array_equal(col, full_ref[1])
+            assert np.array_equal(val.view(np.uint64), full_ref[2].view(np.uint64)), f"assembly {assembly}"
+
+
 @pytest.mark.parametrize("R", [2, 3, 5, 8])
 def test_virtual_rank_partition_matches_single_gpu(ctx, R):
     """The multi-GPU path (row blocks, redundant boundary elements, peer halo stores, allreduced
