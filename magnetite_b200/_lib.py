@@ -16,7 +16,7 @@ from .error import MagnetiteError
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libmagnetite_b200.so"
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAG_OK = 0
 MAG_ERR_CUDA, MAG_ERR_OOM, MAG_ERR_BAD_BC, MAG_ERR_BAD_INDEX = -1, -2, -3, -4
 MAG_ERR_INDEFINITE, MAG_ERR_NOT_CONVERGED, MAG_ERR_NCCL, MAG_ERR_BAD_ARG = -5, -6, -7, -8

@@ -69,13 +69,15 @@ MAG_HD void corner_nodes(const Conn &m, uint32_t local_elem, uint32_t nd[3]) {
     nd[2] = m.n2[e];
 }
 
+constexpr int kFastCols = 12;    // columns of a row table kept in shared memory by the fused kernels (gather.cuh)
+
 // Sorted insert of c into cols[0..n) unless present.  Returns the new count, or -1 when c is new and
-// the list is full.
-MAG_HD int insert_col(uint32_t *cols, int n, uint32_t c) {
+// the list already holds `cap` columns.
+MAG_HD int insert_col(uint32_t *cols, int n, uint32_t c, int cap = kMaxCols) {
     int pos = 0;
     while (pos < n && cols[pos] < c) ++pos;
     if (pos < n && cols[pos] == c) return n;
-    if (n == kMaxCols) return -1;
+    if (n == cap) return -1;
     for (int j = n; j > pos; --j) cols[j] = cols[j - 1];
     cols[pos] = c;
     return n + 1;
@@ -132,13 +134,16 @@ MAG_HD void ke_rows(const Pt *xy, const uint32_t nd[3], int lr, const double *D,
         B[1][2 * k] = z;     B[1][2 * k + 1] = qg[k];
         B[2][2 * k] = qg[k]; B[2][2 * k + 1] = qb[k];
     }
+    // column 2*lr + a of B without a dynamically indexed array (that would put B in local memory on the device)
+    const double qbl = lr == 0 ? qb[0] : (lr == 1 ? qb[1] : qb[2]);
+    const double qgl = lr == 0 ? qg[0] : (lr == 1 ? qg[1] : qg[2]);
     for (int a = 0; a < 2; ++a) {
-        const int r = 2 * lr + a;
-        double btd[3];                                   // row r of B^T D: k ascending, product then sum
+        const double b0 = a ? z : qbl, b1 = a ? qgl : z, b2 = a ? qbl : qgl;      // B[0..3][2*lr + a]
+        double btd[3];                                   // row of B^T D: k ascending, product then sum
         for (int c = 0; c < 3; ++c) {
-            double s = gmul(B[0][r], D[0 * 3 + c]);
-            s = gadd(gmul(B[1][r], D[1 * 3 + c]), s);
-            s = gadd(gmul(B[2][r], D[2 * 3 + c]), s);
+            double s = gmul(b0, D[0 * 3 + c]);
+            s = gadd(gmul(b1, D[1 * 3 + c]), s);
+            s = gadd(gmul(b2, D[2 * 3 + c]), s);
             btd[c] = s;
         }
         for (int c = 0; c < 6; ++c) {
@@ -150,6 +155,71 @@ MAG_HD void ke_rows(const Pt *xy, const uint32_t nd[3], int lr, const double *D,
             out[a][c] = s;
         }
     }
+}
+
+// Visits the 2x2 blocks of one node row in ascending column order WITHOUT any table: for every column the
+// incidence list is walked again and the K_e rows of the matching elements are recomputed (quadratic in the
+// degree, no storage: the path of rows with more columns than a table holds, and of the few rows the
+// reaction forces need).  f(col, a0, a1, a2, a3) receives the accumulated block, row-major.
+template <class Pt, class F>
+MAG_HD void for_each_block_serial(const Conn &m, const Pt *xy, const double *D, double t, const uint32_t *pay,
+                                  uint32_t begin, uint32_t end, F &&f) {
+    uint32_t c = 0;
+    bool have = false;
+    while (next_col(m, pay, begin, end, have, c, &c)) {
+        have = true;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;     // from +0.0, like the reference's zeroed dense matrix
+        for (uint32_t i = begin; i < end; ++i) {
+            const uint32_t p = pay[i], le = p / 3u;
+            const int lr = (int)(p - 3u * le);
+            uint32_t nd[3];
+            corner_nodes(m, le, nd);
+            if (nd[0] != c && nd[1] != c && nd[2] != c) continue;
+            double rows[2][6];
+            ke_rows(xy, nd, lr, D, t, rows);
+            for (int lc = 0; lc < 3; ++lc) {
+                if (nd[lc] != c) continue;
+                a0 = gadd(a0, rows[0][2 * lc]); a1 = gadd(a1, rows[0][2 * lc + 1]);
+                a2 = gadd(a2, rows[1][2 * lc]); a3 = gadd(a3, rows[1][2 * lc + 1]);
+            }
+        }
+        f(c, a0, a1, a2, a3);
+    }
+}
+
+// Row table of one node: cols[0..n) = its distinct column nodes, ascending; acc[4*slot .. 4*slot+4) = the
+// accumulated 2x2 block of column cols[slot], row-major, contributions added in ascending (element, corner)
+// order starting from +0.0 — the reference's `+=` order into a zeroed matrix (solver.rs:295-323).
+// Returns n, or -1 when the row has more than kFastCols columns (cols / acc are then meaningless).
+template <class Pt>
+MAG_HD int build_row_table(const Conn &m, const Pt *xy, const double *D, double t, const uint32_t *pay,
+                           uint32_t begin, uint32_t end, uint32_t *cols, double *acc) {
+    int n = 0;
+    for (uint32_t i = begin; i < end; ++i) {
+        uint32_t nd[3];
+        corner_nodes(m, pay[i] / 3u, nd);
+        for (int k = 0; k < 3; ++k) {
+            n = insert_col(cols, n, nd[k], kFastCols);
+            if (n < 0) return -1;
+        }
+    }
+    for (int j = 0; j < 4 * n; ++j) acc[j] = 0.0;
+    for (uint32_t i = begin; i < end; ++i) {
+        const uint32_t p = pay[i], le = p / 3u;
+        const int lr = (int)(p - 3u * le);
+        uint32_t nd[3];
+        corner_nodes(m, le, nd);
+        double rows[2][6];
+        ke_rows(xy, nd, lr, D, t, rows);
+        for (int lc = 0; lc < 3; ++lc) {
+            int slot = 0;
+            while (cols[slot] != nd[lc]) ++slot;
+            double *a = acc + 4 * slot;
+            a[0] = gadd(a[0], rows[0][2 * lc]); a[1] = gadd(a[1], rows[0][2 * lc + 1]);
+            a[2] = gadd(a[2], rows[1][2 * lc]); a[3] = gadd(a[3], rows[1][2 * lc + 1]);
+        }
+    }
+    return n;
 }
 
 // Writes the block row of one node: bcol[0..ncols) ascending column nodes, bval[4*j..4*j+4) the 2x2
@@ -194,28 +264,13 @@ MAG_HD void fill_row(const Conn &m, const Pt *xy, const double *D, double t, con
         return;
     }
     // a node with more than kMaxCols neighbours: one column at a time, K_e rows recomputed per match
-    uint32_t c = 0;
-    bool have = false;
-    for (uint32_t j = 0; j < ncols && next_col(m, pay, begin, end, have, c, &c); ++j) {
-        have = true;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        for (uint32_t i = begin; i < end; ++i) {
-            const uint32_t p = pay[i], le = p / 3u;
-            const int lr = (int)(p - 3u * le);
-            uint32_t nd[3];
-            corner_nodes(m, le, nd);
-            if (nd[0] != c && nd[1] != c && nd[2] != c) continue;
-            double rows[2][6];
-            ke_rows(xy, nd, lr, D, t, rows);
-            for (int lc = 0; lc < 3; ++lc) {
-                if (nd[lc] != c) continue;
-                const double v0 = rows[0][2 * lc], v1 = rows[0][2 * lc + 1], v2 = rows[1][2 * lc], v3 = rows[1][2 * lc + 1];
-                a0 = gadd(a0, v0); a1 = gadd(a1, v1); a2 = gadd(a2, v2); a3 = gadd(a3, v3);   // from +0.0, like the reference
-            }
-        }
+    uint32_t j = 0;
+    for_each_block_serial(m, xy, D, t, pay, begin, end, [&](uint32_t c, double a0, double a1, double a2, double a3) {
+        if (j >= ncols) return;
         bcol[j] = c;
         bval[4 * j] = a0; bval[4 * j + 1] = a1; bval[4 * j + 2] = a2; bval[4 * j + 3] = a3;
-    }
+        ++j;
+    });
 }
 
 }  // namespace gather

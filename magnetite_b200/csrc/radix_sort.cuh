@@ -20,13 +20,15 @@ constexpr int kRsItems = 16;                       // keys per thread
 constexpr int kRsTile = kRsThreads * kRsItems;     // 4096 keys per CTA
 constexpr int kRadix = 256;
 
-__device__ __forceinline__ uint32_t rs_digit(uint64_t key, int shift) {
+template <class KeyT>
+__device__ __forceinline__ uint32_t rs_digit(KeyT key, int shift) {
     return (uint32_t)(key >> shift) & 0xffu;
 }
 
 // hist[d * n_tiles + tile] = number of keys of the tile whose digit is d.
+template <class KeyT>
 __global__ void __launch_bounds__(kRsThreads)
-rs_hist_kernel(const uint64_t *__restrict__ keys, size_t n, int shift, uint32_t n_tiles,
+rs_hist_kernel(const KeyT *__restrict__ keys, size_t n, int shift, uint32_t n_tiles,
                uint32_t *__restrict__ hist) {
     __shared__ uint32_t cnt[kRadix];
     cnt[threadIdx.x] = 0;
@@ -45,14 +47,15 @@ rs_hist_kernel(const uint64_t *__restrict__ keys, size_t n, int shift, uint32_t 
     hist[(size_t)threadIdx.x * n_tiles + blockIdx.x] = cnt[threadIdx.x];
 }
 
-// Dynamic shared memory: staged keys (tile*8 B) then staged payloads (tile*4 B).
+// Dynamic shared memory: staged keys (tile*sizeof(KeyT)) then staged payloads (tile*4 B).
+template <class KeyT>
 __global__ void __launch_bounds__(kRsThreads)
-rs_scatter_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ pin,
-                  uint64_t *__restrict__ kout, uint32_t *__restrict__ pout, size_t n, int shift,
+rs_scatter_kernel(const KeyT *__restrict__ kin, const uint32_t *__restrict__ pin,
+                  KeyT *__restrict__ kout, uint32_t *__restrict__ pout, size_t n, int shift,
                   uint32_t n_tiles, const uint32_t *__restrict__ offs) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
-    uint64_t *skey = reinterpret_cast<uint64_t *>(rs_smem);
-    uint32_t *spay = reinterpret_cast<uint32_t *>(rs_smem + (size_t)kRsTile * sizeof(uint64_t));
+    KeyT *skey = reinterpret_cast<KeyT *>(rs_smem);
+    uint32_t *spay = reinterpret_cast<uint32_t *>(rs_smem + (size_t)kRsTile * sizeof(KeyT));
     __shared__ uint32_t warp_cnt[kRsWarps][kRadix];   // running per-warp digit counts
     __shared__ uint32_t digit_base[kRadix];           // first staged slot of each digit
     __shared__ uint32_t global_base[kRadix];          // first output slot of each digit
@@ -69,14 +72,14 @@ rs_scatter_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__
     // the 32 consecutive items starting at w*512 + i*32.
     const uint32_t wbase = warp * (kRsItems * 32);
 
-    uint64_t key[kRsItems];
+    KeyT key[kRsItems];
     uint32_t pay[kRsItems];
     uint32_t rank[kRsItems];
 #pragma unroll
     for (int i = 0; i < kRsItems; ++i) {
         const uint32_t t = wbase + i * 32 + lane;
         const bool ok = t < tile_n;
-        key[i] = ok ? kin[tile_base + t] : 0ull;
+        key[i] = ok ? kin[tile_base + t] : (KeyT)0;
         pay[i] = ok ? pin[tile_base + t] : 0u;
     }
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -128,7 +131,7 @@ rs_scatter_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__
     __syncthreads();
 
     for (uint32_t j = threadIdx.x; j < tile_n; j += kRsThreads) {
-        const uint64_t k = skey[j];
+        const KeyT k = skey[j];
         const uint32_t d = rs_digit(k, shift);
         const size_t g = (size_t)global_base[d] + (j - digit_base[d]);
         kout[g] = k;
@@ -136,37 +139,39 @@ rs_scatter_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__
     }
 }
 
-constexpr size_t kRsSmemBytes = (size_t)kRsTile * (sizeof(uint64_t) + sizeof(uint32_t));
-
-// Sorts n pairs by the low `key_bits` bits of the key.  keys/payload hold the
-// input and receive the output; keys_alt/payload_alt are scratch of equal size.
-inline void radix_sort_pairs(mag_ctx *ctx, uint64_t *keys, uint32_t *payload, uint64_t *keys_alt,
+// Sorts n pairs by the low `key_bits` bits of the key (uint64 COO keys, or uint32 node ids: a third less
+// traffic per pass).  keys/payload hold the input and receive the output; keys_alt/payload_alt are scratch
+// of equal size.
+template <class KeyT>
+inline void radix_sort_pairs(mag_ctx *ctx, KeyT *keys, uint32_t *payload, KeyT *keys_alt,
                              uint32_t *payload_alt, size_t n, int key_bits) {
     if (n < 2 || key_bits <= 0) return;
     if (n > 0xffffffffull) fail(MAG_ERR_BAD_ARG, "radix_sort_pairs: more than 2^32 pairs");
-    if (!ctx->rs_attr_set) {      // a per-device attribute: kept per context, not per process
-        MAG_CUDA(cudaFuncSetAttribute(rs_scatter_kernel,
+    constexpr size_t kRsSmemBytes = (size_t)kRsTile * (sizeof(KeyT) + sizeof(uint32_t));
+    bool &attr_set = sizeof(KeyT) == 8 ? ctx->rs_attr_set : ctx->rs32_attr_set;
+    if (!attr_set) {              // a per-device attribute: kept per context, not per process
+        MAG_CUDA(cudaFuncSetAttribute(rs_scatter_kernel<KeyT>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kRsSmemBytes));
-        ctx->rs_attr_set = true;
+        attr_set = true;
     }
     const uint32_t n_tiles = cdiv(n, kRsTile);
     const size_t hist_n = (size_t)kRadix * n_tiles;
     DevBuf<uint32_t> hist(ctx, hist_n);
     int passes = (key_bits + 7) / 8;
-    uint64_t *kin = keys, *kout = keys_alt;
+    KeyT *kin = keys, *kout = keys_alt;
     uint32_t *pin = payload, *pout = payload_alt;
     for (int p = 0; p < passes; ++p) {
         const int shift = 8 * p;
-        MAG_LAUNCH(ctx, rs_hist_kernel, n_tiles, kRsThreads, 0, kin, n, shift, n_tiles, hist.p);
+        MAG_LAUNCH(ctx, rs_hist_kernel<KeyT>, n_tiles, kRsThreads, 0, (const KeyT *)kin, n, shift, n_tiles, hist.p);
         exclusive_scan_u32(ctx, hist.p, hist_n, hist.p, hist_n);
-        MAG_LAUNCH(ctx, rs_scatter_kernel, n_tiles, kRsThreads, kRsSmemBytes, kin, pin, kout, pout,
-                   n, shift, n_tiles, (const uint32_t *)hist.p);
+        MAG_LAUNCH(ctx, rs_scatter_kernel<KeyT>, n_tiles, kRsThreads, kRsSmemBytes, (const KeyT *)kin,
+                   (const uint32_t *)pin, kout, pout, n, shift, n_tiles, (const uint32_t *)hist.p);
         std::swap(kin, kout);
         std::swap(pin, pout);
     }
     if (kin != keys) {   // odd number of passes: result sits in the alt buffers
-        MAG_CUDA(cudaMemcpyAsync(keys, kin, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        MAG_CUDA(cudaMemcpyAsync(keys, kin, n * sizeof(KeyT), cudaMemcpyDeviceToDevice, ctx->stream));
         MAG_CUDA(cudaMemcpyAsync(payload, pin, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
     }
 }

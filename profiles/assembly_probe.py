@@ -1,8 +1,9 @@
-"""Sorted-key assembly (mag_options.assembly = 0, the default) against the gather assembly (assembly = 1) on
-the device-resident plate:  python profiles/assembly_probe.py [nx ny reps]   (default 4000 2000 3 = 16 M DOF)
+"""The three assembly modes of mag_options.assembly on the device-resident plate — 0 fused gather (default),
+1 gather into block rows + elimination kernels, 2 sorted COO keys + segmented reduction + elimination kernels:
+    python profiles/assembly_probe.py [nx ny reps [modes]]   (default 4000 2000 3 012 = 16 M DOF, all modes)
 
 Prints the library's phase timers (CUDA events on its stream) for every repetition and checks at full size
-that both paths leave the same K_ff: same counts, and the order-preserving CSR SpMV of both systems on one
+that all paths leave the same K_ff: same counts, and the order-preserving CSR SpMV of the systems on one
 random vector gives bit-identical results."""
 import ctypes as C
 import json
@@ -19,6 +20,8 @@ PHASES = ("ms_upload", "ms_elem", "ms_sort", "ms_reduce", "ms_bc", "ms_format", 
 
 def main():
     nx, ny, reps = (int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (4000, 2000, 3)
+    modes = [int(c) for c in (sys.argv[4] if len(sys.argv) > 4 else "012")]
+    names = {0: "fused gather", 1: "gather + eliminate", 2: "sorted keys"}
     lib = _lib.load()
     ctx = _lib.Context(0)
     mat = solver._material(meshgen.EXAMPLE_MATERIAL)
@@ -37,7 +40,7 @@ def main():
         return sysh, st.as_dict()
 
     wdm, wview = plate(256, 128)                       # warm-up: module load, heap slabs
-    for a in (0, 1):
+    for a in modes:
         s, _ = assemble(wview, a)
         lib.mag_system_free(s)
     lib.mag_devmesh_free(wdm)
@@ -45,11 +48,11 @@ def main():
     dm, view = plate(nx, ny)
     n_elems = int(view.n_elems)
     keep = {}
-    for a in (0, 1):
+    for a in modes:
         for rep in range(reps):
             s, st = assemble(view, a)
             asm_ms = sum(st[k] for k in ("ms_elem", "ms_sort", "ms_reduce", "ms_bc"))
-            row = {"assembly": "gather" if a else "sorted keys", "rep": rep, "elements": n_elems,
+            row = {"assembly": names[a], "rep": rep, "elements": n_elems,
                    "assembly_ms": round(asm_ms, 3), "melem_per_s": round(n_elems / asm_ms / 1e3, 1),
                    "n_free": int(st["n_free"]), "nnz": int(st["nnz"]), "nnz_structural": int(st["nnz_structural"]),
                    "launches": int(st["kernel_launches"])}
@@ -59,17 +62,19 @@ def main():
                 keep[a] = (s, st)
             else:
                 lib.mag_system_free(s)
-    (s0, st0), (s1, st1) = keep[0], keep[1]
-    same_counts = all(int(st0[k]) == int(st1[k]) for k in ("n_free", "nnz", "nnz_structural", "sell_entries"))
-    n_free = int(st0["n_free"])
+    n_free = int(keep[modes[0]][1]["n_free"])
     x = np.random.default_rng(1).normal(size=n_free)
-    y0, y1 = np.empty(n_free), np.empty(n_free)
-    _lib.check(lib.mag_system_spmv(s0, 1, _lib.ptr(x), _lib.ptr(y0)), "spmv(sorted keys)")
-    _lib.check(lib.mag_system_spmv(s1, 1, _lib.ptr(x), _lib.ptr(y1)), "spmv(gather)")
-    print(json.dumps({"same_counts": bool(same_counts), "csr_spmv_bit_identical": bool(np.array_equal(y0, y1)),
-                      "spmv_norm": float(np.linalg.norm(y0))}), flush=True)
-    lib.mag_system_free(s0)
-    lib.mag_system_free(s1)
+    ys = {}
+    for a in modes:
+        ys[a] = np.empty(n_free)
+        _lib.check(lib.mag_system_spmv(keep[a][0], 1, _lib.ptr(x), _lib.ptr(ys[a])), f"spmv({names[a]})")
+    st0 = keep[modes[0]][1]
+    same_counts = all(int(st0[k]) == int(keep[a][1][k]) for a in modes for k in ("n_free", "nnz", "nnz_structural", "sell_entries"))
+    print(json.dumps({"modes": [names[a] for a in modes], "same_counts": bool(same_counts),
+                      "csr_spmv_bit_identical": bool(all(np.array_equal(ys[modes[0]], ys[a]) for a in modes)),
+                      "spmv_norm": float(np.linalg.norm(ys[modes[0]]))}), flush=True)
+    for a in modes:
+        lib.mag_system_free(keep[a][0])
     lib.mag_devmesh_free(dm)
     ctx.close()
 

@@ -1,6 +1,6 @@
 //! Thin `extern "C"` binding of libmagnetite_b200.so plus a safe wrapper with the exact
 //! signature of the reference's `solver::run` (src/solver.rs:543-547), so `main.rs:64`
-//! only changes its `use`.  Mirrors include/magnetite_b200.h (ABI version 2).
+//! only changes its `use`.  Mirrors include/magnetite_b200.h (ABI version 3).
 //!
 //! UNVERIFIED: there is no Rust toolchain in the build image; this file has never been
 //! compiled.  The Python ctypes binding (magnetite_b200/_lib.py) exercises the same ABI.

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(built):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in the header but not exported"
     assert sorted(_lib.declared_symbols()) == syms, "ctypes prototypes drifted from the header"
-    assert lib.mag_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.mag_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header(built):

@@ -1,7 +1,14 @@
-"""GPU: the gather assembly (mag_options.assembly = 1, csrc/gather.cuh) leaves exactly what the sorted-key
-assembly leaves — the full K, K_ff, the rhs and the DOF maps bit for bit — hence bit-identical solves, for
-whole meshes and for the row blocks of the partitioned path.  The per-node core is also checked against the
-oracle on the CPU (tests/test_gather_core_host.py); the default path against the oracle in test_gpu_parity.py."""
+"""GPU: the three assembly modes of mag_options.assembly leave exactly the same system — the full K, K_ff, the
+rhs and the DOF maps bit for bit — hence bit-identical solves, for whole meshes and for the row blocks of the
+partitioned path:  0 (default) fused gather: node rows built in shared memory and eliminated in the same kernel,
+K never stored;  1 gather into 2x2-block rows, then the elimination kernels;  2 COO keys, stable sort, segmented
+reduction, then the elimination kernels.
+
+This file compares GPU paths with each other.  Their link to the ORACLE is transitive and stated here on purpose:
+the per-node cores every gather kernel calls (gather_core.h: fill_row, build_row_table, for_each_block_serial) are
+compiled by g++ into tests/test_gather_core_host.py and compared there with the oracle bit for bit, and the
+default mode (0) is what every test of tests/test_gpu_parity.py runs against the oracle and the golden fixtures
+(MAGNETITE_B200_TEST_ASSEMBLY=1|2 runs that whole suite against the other two)."""
 from pathlib import Path
 
 import numpy as np
@@ -40,56 +47,67 @@ MESHES = {
     "jitter_31x19": lambda: meshgen.jitter(meshgen.plate(31, 19)),
     "perforated_96x48": lambda: meshgen.perforated_plate(96, 48, pitch=16, radius=4),
     "plate_257x65": lambda: meshgen.plate(257, 65),
-    "fan_40": _fan,
+    "fan_40": _fan,                                      # 41 columns in the hub row: the table-free traversal
+    "fan_12": lambda: _fan(12),                          # 13 columns: one past the shared-memory row table
+    "fan_11": lambda: _fan(11),                          # 12 columns: the table's last size
     "example_linkedin": lambda: _example("example_linkedin"),
     "example_tensile": lambda: _example("example_tensile"),
 }
 
 
+def _bits(a):
+    return a.view(np.uint64) if a.dtype == np.float64 else a
+
+
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("name", list(MESHES))
-def test_gather_assembly_is_bit_identical_to_the_sorted_key_assembly(ctx, name):
+def test_gather_assemblies_are_bit_identical_to_the_sorted_key_assembly(ctx, name, mode):
     mesh = MESHES[name]()
-    with solver.System(mesh, META, ctx) as A, solver.System(mesh, META, ctx, options=_lib.default_options(assembly=1)) as G:
+    jac = dict(precond=1)                                           # the same solver on both sides
+    with solver.System(mesh, META, ctx, options=_lib.default_options(assembly=2)) as A, \
+            solver.System(mesh, META, ctx, options=_lib.default_options(assembly=mode)) as G:
         assert (G.n_free, G.nnz, G.nnz_structural) == (A.n_free, A.nnz, A.nnz_structural)
         for a, g in zip(A.export_full(), G.export_full()):
-            assert np.array_equal(a, g)
+            assert np.array_equal(_bits(a), _bits(g))
         for a, g in zip(A.export_kff(), G.export_kff()):
-            assert np.array_equal(a, g)
-        sa, sg = A.solve(_lib.default_options()), G.solve(_lib.default_options(assembly=1))
+            assert np.array_equal(_bits(a), _bits(g))
+        sa, sg = A.solve(_lib.default_options(assembly=2, **jac)), G.solve(_lib.default_options(assembly=mode, **jac))
     for k in ("ux", "uy", "fx", "fy", "stress"):
         assert np.array_equal(getattr(sa, k), getattr(sg, k)), k
     assert sa.stats["iters"] == sg.stats["iters"]
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("R", [2, 5])
-def test_gather_assembly_on_row_blocks(ctx, R):
+def test_gather_assemblies_on_row_blocks(ctx, R, mode):
     """The partitioned path (element lists, owned node ranges) through R virtual ranks on one GPU."""
     mesh = meshgen.jitter(meshgen.plate(48, 21))
-    a = solver.virtual_rank_solve(mesh, META, R, ctx, _lib.default_options())
-    g = solver.virtual_rank_solve(mesh, META, R, ctx, _lib.default_options(assembly=1))
+    a = solver.virtual_rank_solve(mesh, META, R, ctx, _lib.default_options(assembly=2, precond=1))
+    g = solver.virtual_rank_solve(mesh, META, R, ctx, _lib.default_options(assembly=mode, precond=1))
     for k in ("ux", "uy", "fx", "fy", "stress"):
         assert np.array_equal(getattr(a, k), getattr(g, k)), k
-    one = solver.solve_soa(mesh, META, ctx, _lib.default_options(assembly=1, rel_tol=1e-12))
-    tight = solver.virtual_rank_solve(mesh, META, R, ctx, _lib.default_options(assembly=1, rel_tol=1e-12))
+    one = solver.solve_soa(mesh, META, ctx, _lib.default_options(assembly=mode, rel_tol=1e-12))
+    tight = solver.virtual_rank_solve(mesh, META, R, ctx, _lib.default_options(assembly=mode, rel_tol=1e-12))
     u1, ur = np.concatenate([one.ux, one.uy]), np.concatenate([tight.ux, tight.uy])
     assert np.linalg.norm(ur - u1) / np.linalg.norm(u1) < 1e-9
 
 
-def test_gather_assembly_through_mag_solve_and_empty_mesh(ctx):
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gather_assemblies_through_mag_solve_and_empty_mesh(ctx, mode):
     mesh = meshgen.plate(24, 12)
-    a = solver.solve_soa(mesh, META, ctx, _lib.default_options(compat=1))
-    g = solver.solve_soa(mesh, META, ctx, _lib.default_options(compat=1, assembly=1))
+    a = solver.solve_soa(mesh, META, ctx, _lib.default_options(compat=1, assembly=2))
+    g = solver.solve_soa(mesh, META, ctx, _lib.default_options(compat=1, assembly=mode))
     for k in ("ux", "uy", "fx", "fy", "stress"):
         assert np.array_equal(getattr(a, k), getattr(g, k)), k
     empty = MeshSoA(*(np.zeros(0, t) for t in (np.float64, np.float64, np.uint32, np.uint32, np.uint32, np.float64,
                                                  np.float64, np.float64, np.float64, np.uint8)))
-    sol = solver.solve_soa(empty, META, ctx, _lib.default_options(assembly=1))
+    sol = solver.solve_soa(empty, META, ctx, _lib.default_options(assembly=mode))
     assert sol.ux.size == 0 and sol.stress.size == 0 and sol.stats["iters"] == 0
     # an isolated node that no element references has an empty incidence list and keeps an empty matrix row
     iso = meshgen.plate(4, 3).copy()
     iso = MeshSoA(np.append(iso.x, 99.0), np.append(iso.y, 99.0), iso.n0, iso.n1, iso.n2, np.append(iso.ux, 0.0),
                   np.append(iso.uy, 0.0), np.append(iso.fx, 0.0), np.append(iso.fy, 0.0), np.append(iso.known, 3).astype(np.uint8))
-    a = solver.solve_soa(iso, META, ctx, _lib.default_options(compat=1))
-    g = solver.solve_soa(iso, META, ctx, _lib.default_options(compat=1, assembly=1))
+    a = solver.solve_soa(iso, META, ctx, _lib.default_options(compat=1, assembly=2))
+    g = solver.solve_soa(iso, META, ctx, _lib.default_options(compat=1, assembly=mode))
     for k in ("ux", "uy", "fx", "fy", "stress"):
         assert np.array_equal(getattr(a, k), getattr(g, k)), k
