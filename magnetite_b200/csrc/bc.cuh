@@ -39,6 +39,15 @@ __global__ void dof_flags_kernel(const uint8_t *__restrict__ known, size_t n_dof
     if (rf != cf) *unpaired = 1;
 }
 
+// colid[d] = reduced column of DOF d, or 0xffffffff where the displacement is prescribed (one 8-byte load per
+// column node tells the fused assembly both the column ids and the prescribed flags).
+__global__ void col_ids_kernel(const uint8_t *__restrict__ known, const uint32_t *__restrict__ colmap, size_t n_dof,
+                               uint32_t *__restrict__ colid) {
+    const size_t d = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_dof) return;
+    colid[d] = dof_u_known(known, (uint32_t)d) ? 0xffffffffu : colmap[d];
+}
+
 // Pass 1 (fill == 0): count kept entries of every owned reduced row.
 // Pass 2 (fill == 1): write col/val, the rhs and the diagonal.
 // One thread per owned DOF; its BSR row is walked in ascending column order.

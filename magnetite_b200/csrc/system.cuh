@@ -42,6 +42,7 @@ struct mag_system {
     mag::DevBuf<uint32_t> elist;             // multi-rank: the elements touching an owned node (ascending)
     size_t n_local_elems = 0;
     mag::DevBuf<uint32_t> rowmap, colmap;    // n_dof+1 each (global; last = total)
+    mag::DevBuf<uint32_t> colid;             // n_dof: reduced column, or ~0 where the displacement is prescribed
     mag::CsrMatrix Kff;                      // owned rows x global cols
     mag::DevBuf<double> rhs, diag;           // owned rows
     mag::SellMatrix sell;
@@ -243,35 +244,77 @@ static void assemble_impl(mag_ctx *ctx, const mag_mesh *m, const mag_material *m
     const uint32_t n_owned_dof = 2 * n_own;
 
     if (asm_mode == 0) {
-        // ---- fused gather (gather.cuh): incidence lists -> row tables in shared memory -> K_ff --------
-        st.ms_elem = phase.stop();                  // only the rank's element list: K_e rows are recomputed per node row
+        // ---- fused gather (gather.cuh): K_e per triangle, incidence lists, row tables in shared memory -> K_ff
+        DevBuf<double> kblk(ctx, El * 36);
+        if (El)
+            MAG_LAUNCH(ctx, element_stiffness_kernel, cdiv(El, kElemThreads), kElemThreads, 0,
+                       (const double2 *)S->xy.p, (const uint32_t *)S->n0.p, (const uint32_t *)S->n1.p,
+                       (const uint32_t *)S->n2.p, elist_p, El, 1, kblk.p);
+        st.ms_elem = phase.stop();
         phase.start();
         build_incidence(ctx, S->n0, S->n1, S->n2, elist_p, El, N, S->node_lo, S->node_hi, S->inc);
         st.ms_sort = phase.stop();
 
         phase.start();
-        const ElimView EV{S->known.p, S->rowmap.p, S->colmap.p, S->bc_ux.p, S->bc_uy.p, S->bc_fx.p, S->bc_fy.p,
-                          drop, A.row_lo, S->node_lo};
-        DevBuf<unsigned long long> n_blocks(ctx, 1);
-        n_blocks.zero();
+        S->colid.alloc(ctx, n_dof + 2);
+        if (n_dof)
+            MAG_LAUNCH(ctx, col_ids_kernel, cdiv(n_dof, 256), 256, 0, (const uint8_t *)S->known.p,
+                       (const uint32_t *)S->colmap.p, n_dof, S->colid.p);
+        S->diag.zero();                             // the fill pass writes the diagonal where it keeps one
+        const ElimView EV{S->known.p, S->rowmap.p, S->colmap.p, reinterpret_cast<const uint2 *>(S->colid.p),
+                          S->bc_ux.p, S->bc_uy.p, S->bc_fx.p, S->bc_fy.p, drop, A.row_lo, S->node_lo};
+        DevBuf<unsigned long long> counters(ctx, 2);            // [0] structural blocks, [1] nnz (one-pass kernel)
+        counters.zero();
         A.rowptr.zero();
-        launch_fused_rows<0>(ctx, S->xy, S->n0, S->n1, S->n2, elist_p, S->inc, n_own, EV, A.rowptr.p, nullptr, nullptr,
-                             nullptr, nullptr, nullptr, n_blocks.p);
-        exclusive_scan_u32(ctx, A.rowptr.p, n_rows, A.rowptr.p, (size_t)n_rows + 1);
-        unsigned long long h_blocks = 0;
-        uint32_t h_nnz = 0;
-        MAG_CUDA(cudaMemcpyAsync(&h_blocks, n_blocks.p, sizeof h_blocks, cudaMemcpyDeviceToHost, ctx->stream));
-        MAG_CUDA(cudaMemcpyAsync(&h_nnz, A.rowptr.p + n_rows, sizeof h_nnz, cudaMemcpyDeviceToHost, ctx->stream));
-        MAG_CUDA(cudaStreamSynchronize(ctx->stream));
-        A.nnz = h_nnz;
-        K.n_blocks = (uint32_t)h_blocks;            // structural size only: the block rows themselves are not stored
-        st.ms_reduce = phase.stop();
-
-        phase.start();
-        A.col.alloc(ctx, A.nnz);
-        A.val.alloc(ctx, A.nnz);
-        launch_fused_rows<1>(ctx, S->xy, S->n0, S->n1, S->n2, elist_p, S->inc, n_own, EV, nullptr,
-                             (const uint32_t *)A.rowptr.p, A.col.p, A.val.p, S->rhs.p, S->diag.p, nullptr);
+        unsigned long long h_counters[2] = {0, 0};
+        if (ctx->tune & 64) {
+            // MAG_TUNE=64: two passes (count -> scan -> fill) instead of the one-pass kernel (comparison / fallback)
+            launch_fused_rows<0>(ctx, S->xy, S->n0, S->n1, S->n2, elist_p, kblk.p, S->inc, n_own, EV, A.rowptr.p, nullptr,
+                                 nullptr, nullptr, nullptr, nullptr, counters.p);
+            exclusive_scan_u32(ctx, A.rowptr.p, n_rows, A.rowptr.p, (size_t)n_rows + 1);
+            uint32_t h_nnz = 0;
+            MAG_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+            MAG_CUDA(cudaMemcpyAsync(&h_nnz, A.rowptr.p + n_rows, sizeof h_nnz, cudaMemcpyDeviceToHost, ctx->stream));
+            MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+            A.nnz = h_nnz;
+            st.ms_reduce = phase.stop();
+            phase.start();
+            A.col.alloc(ctx, A.nnz);
+            A.val.alloc(ctx, A.nnz);
+            launch_fused_rows<1>(ctx, S->xy, S->n0, S->n1, S->n2, elist_p, kblk.p, S->inc, n_own, EV, nullptr,
+                                 (const uint32_t *)A.rowptr.p, A.col.p, A.val.p, S->rhs.p, S->diag.p, nullptr);
+        } else {
+            // one pass: the tiles find their place in the CSR arrays by decoupled look-back.  Capacity: a node with d
+            // incident triangles has at most 2d + 1 column nodes, so K_ff has at most 4 * (2 * 3 * El + n_own) entries;
+            // the arrays are cut back to nnz afterwards.
+            const size_t cap = 4 * (6 * (size_t)El + (size_t)n_own);
+            if (cap >= (1ull << 32)) fail(MAG_ERR_BAD_ARG, "this rank's K_ff could reach %zu entries; the CSR offsets are 32-bit: use more GPUs", cap);
+            A.col.alloc(ctx, cap);
+            A.val.alloc(ctx, cap);
+            const unsigned tiles = cdiv(n_own, kFusedThreads);
+            DevBuf<unsigned long long> status(ctx, (size_t)tiles + 1);
+            DevBuf<unsigned> ticket(ctx, 1);
+            DevBuf<int> err(ctx, 1);
+            status.zero(); ticket.zero(); err.zero();
+            if (n_own) {
+                ensure_fused_attrs(ctx);
+                const TileScan T{status.p, ticket.p, counters.p + 1, err.p};
+                MAG_LAUNCH(ctx, fused_rows_onepass_kernel, tiles, kFusedThreads, kFusedSmem, (const double2 *)S->xy.p,
+                           (const uint32_t *)S->n0.p, (const uint32_t *)S->n1.p, (const uint32_t *)S->n2.p, elist_p,
+                           (const double *)kblk.p, (const uint32_t *)S->inc.pay.p, (const uint32_t *)S->inc.nptr.p, n_own,
+                           n_rows, EV, A.rowptr.p, A.col.p, A.val.p, S->rhs.p, S->diag.p, counters.p, T);
+            }
+            int h_err = 0;
+            MAG_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof h_counters, cudaMemcpyDeviceToHost, ctx->stream));
+            MAG_CUDA(cudaMemcpyAsync(&h_err, err.p, sizeof h_err, cudaMemcpyDeviceToHost, ctx->stream));
+            MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (h_err) fail(MAG_ERR_CUDA, "fused assembly: a tile never published its row count (look-back guard tripped)");
+            A.nnz = h_counters[1];
+            A.col.shrink(A.nnz);
+            A.val.shrink(A.nnz);
+            st.ms_reduce = 0.f;
+        }
+        K.n_blocks = (uint32_t)h_counters[0];       // structural size only: the block rows themselves are not stored
         S->has_K = false;
     } else {
         if (asm_mode == 1) {

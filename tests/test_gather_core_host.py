@@ -121,8 +121,8 @@ MESHES = {
     "fan_40": _fan,
     "fan_17": lambda: _fan(17),             # 18 columns in the hub row: just past kMaxCols
     "fan_15": lambda: _fan(15),             # 16 columns: the last size the thread-local path takes
-    "fan_11": lambda: _fan(11),             # 12 columns: the last size the shared-memory row table takes
-    "fan_12": lambda: _fan(12),             # 13 columns: the first row of the table-free traversal
+    "fan_10": lambda: _fan(10),             # 11 columns: the last size the shared-memory row table takes
+    "fan_11": lambda: _fan(11),             # 12 columns: the first row of the table-free traversal
     "degenerate": _degenerate,
     "example_linkedin": lambda: _example("example_linkedin"),      # Delaunay mesh in gmsh-like order
     "example_tensile": lambda: _example("example_tensile"),        # all clockwise after check_ccw
@@ -132,7 +132,7 @@ MESHES = {
 @pytest.mark.parametrize("core", ["fill_row", "row_table"])
 @pytest.mark.parametrize("name", list(MESHES))
 def test_gather_core_matches_the_oracle_bit_for_bit(harness, name, core):
-    # fill_row: the core of gather_fill_kernel (assembly = 1); row_table: build_row_table (<= kFastCols = 12 columns)
+    # fill_row: the core of gather_fill_kernel (assembly = 1); row_table: build_row_table (<= kFastCols = 11 columns)
     # and for_each_block_serial beyond, the cores of the fused default assembly and of the reaction rows
     harness.gather_host_set_mode(0 if core == "fill_row" else 1)
     mesh = MESHES[name]()

@@ -48,8 +48,8 @@ MESHES = {
     "perforated_96x48": lambda: meshgen.perforated_plate(96, 48, pitch=16, radius=4),
     "plate_257x65": lambda: meshgen.plate(257, 65),
     "fan_40": _fan,                                      # 41 columns in the hub row: the table-free traversal
-    "fan_12": lambda: _fan(12),                          # 13 columns: one past the shared-memory row table
-    "fan_11": lambda: _fan(11),                          # 12 columns: the table's last size
+    "fan_11": lambda: _fan(11),                          # 12 columns: one past the shared-memory row table
+    "fan_10": lambda: _fan(10),                          # 11 columns: the table's last size
     "example_linkedin": lambda: _example("example_linkedin"),
     "example_tensile": lambda: _example("example_tensile"),
 }
