@@ -525,7 +525,7 @@ def run_ours(args):
     assemblies = None
     if world == 1 and not args.no_extras:
         assemblies = {}
-        for name, mode in (("fused_gather", 0), ("gather_bsr_then_eliminate", 1), ("sorted_coo_keys", 2)):
+        for name, mode in (("gather", 0), ("sorted_coo_keys", 1)):
             try:
                 og = options(assembly=mode)
                 g_ms, g_st = [], None

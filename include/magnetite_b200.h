@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MAG_ABI_VERSION 3   /* 3: mag_options.assembly 0/1/2 renumbered (0 = fused gather); mag_system_residual */
+#define MAG_ABI_VERSION 3   /* 3: mag_options.assembly renumbered (0 = gather, now the default; 1 = sorted COO keys); mag_system_residual */
 
 /* src/solver.rs:17-19 */
 #define MAG_DOF 2
@@ -89,13 +89,12 @@ typedef struct {
     int32_t want_sigma;      /* also return sx,sy,txy per element                      */
     int32_t allreduce;       /* multi-GPU dot products: 0 peer-memory mailbox (default), 1 NCCL  */
     int32_t coarse_aggregates; /* precond 2: number of aggregates (0 = auto, at most 2048)       */
-    int32_t assembly;        /* how K_ff is built; every mode leaves the same K, K_ff and rhs bit for bit.
-                              * 0 (default): fused gather — per-node incidence lists (3 sorted pairs per triangle),
-                              *    node rows built in shared memory from recomputed K_e rows and eliminated in the same
-                              *    kernel; K itself is never stored (the parity export rebuilds it);
-                              * 1: gather into 2x2-block rows of K, then the elimination kernels;
-                              * 2: the north star's wording — 9 COO keys per triangle, stable sort, warp-shuffle
-                              *    segmented reduction, then the elimination kernels */
+    int32_t assembly;        /* how the full K (2x2-block CSR) is built; both modes leave the same K, K_ff, rhs bit for bit.
+                              * 0 (default): gather — 3 (node, incidence) pairs per triangle sorted by node, then one
+                              *    thread per node row adds the recomputed K_e rows of its incident triangles;
+                              * 1: the north star's wording — K_e per triangle, 9 COO keys per triangle, stable sort,
+                              *    warp-shuffle segmented reduction.
+                              * (ABI 2 had them the other way round: 0 sorted keys, 1 gather.) */
     void *stream;            /* cudaStream_t to run on, or NULL for the ctx's own      */
 } mag_options;
 

@@ -255,15 +255,7 @@ extern "C" int mag_system_export_full(const mag_system *sys, int64_t *rowptr, in
         if (!sys || !rowptr || !col || !val) fail(MAG_ERR_BAD_ARG, "null argument");
         mag_ctx *ctx = sys->ctx;
         CallScope scope(ctx, nullptr);
-        BsrMatrix rebuilt;           // the fused assembly never stores K: rebuild the block rows for the export
-        if (!sys->has_K) {
-            rebuilt.node_lo = sys->K.node_lo; rebuilt.node_hi = sys->K.node_hi;
-            upload_material(ctx, sys->mat);
-            build_bsr_from_incidence(ctx, sys->xy, sys->n0, sys->n1, sys->n2,
-                                     sys->nranks > 1 ? (const uint32_t *)sys->elist.p : (const uint32_t *)nullptr,
-                                     sys->inc, rebuilt);
-        }
-        const BsrMatrix &K = sys->has_K ? sys->K : rebuilt;
+        const BsrMatrix &K = sys->K;
         const uint32_t n_own = K.node_hi - K.node_lo;
         const size_t nnz = (size_t)K.n_blocks * 4, n_rows = 2 * (size_t)n_own;
         DevBuf<int64_t> d_rowptr(ctx, n_rows + 1);

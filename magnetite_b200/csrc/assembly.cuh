@@ -67,8 +67,8 @@ __global__ void mark_heads_kernel(const uint64_t *__restrict__ keys, size_t n, i
 __global__ void __launch_bounds__(256)
 segment_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ payload,
                       const uint32_t *__restrict__ head, const uint32_t *__restrict__ uid,
-                      size_t n_valid, int bits, const double *__restrict__ kblk,
-                      uint32_t *__restrict__ bcol, double *__restrict__ bval) {
+                      size_t n_valid, int bits, uint32_t node_lo, const double *__restrict__ kblk,
+                      uint32_t *__restrict__ brow, uint32_t *__restrict__ bcol, double *__restrict__ bval) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool ok = i < n_valid;
@@ -113,6 +113,7 @@ segment_reduce_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restr
     }
     if (is_head) {
         const uint32_t u = uid[i];
+        brow[u] = (uint32_t)(key >> bits) - node_lo;
         bcol[u] = (uint32_t)(key & ((1ull << bits) - 1ull));
         double2 *dst = reinterpret_cast<double2 *>(bval + (size_t)u * 4);
         dst[0] = make_double2(a0, a1);
@@ -125,6 +126,7 @@ struct BsrMatrix {
     uint32_t node_lo = 0, node_hi = 0;   // owned node rows [lo, hi)
     uint32_t n_blocks = 0;
     DevBuf<uint32_t> browptr;            // (hi-lo)+1
+    DevBuf<uint32_t> brow;               // n_blocks, LOCAL row node (node - node_lo) of every block
     DevBuf<uint32_t> bcol;               // n_blocks, global node ids, ascending per row
     DevBuf<double> bval;                 // n_blocks*4, row-major 2x2
 };

@@ -69,8 +69,6 @@ MAG_HD void corner_nodes(const Conn &m, uint32_t local_elem, uint32_t nd[3]) {
     nd[2] = m.n2[e];
 }
 
-constexpr int kFastCols = 11;    // columns of a row table kept in shared memory by the fused kernels (gather.cuh)
-
 // Sorted insert of c into cols[0..n) unless present.  Returns the new count, or -1 when c is new and
 // the list already holds `cap` columns.
 MAG_HD int insert_col(uint32_t *cols, int n, uint32_t c, int cap = kMaxCols) {
@@ -185,72 +183,6 @@ MAG_HD void for_each_block_serial(const Conn &m, const Pt *xy, const double *D, 
         }
         f(c, a0, a1, a2, a3);
     }
-}
-
-// Row table of one node: cols[0..n) = its distinct column nodes, ascending; acc[4*slot .. 4*slot+4) = the
-// accumulated 2x2 block of column cols[slot], row-major, contributions added in ascending (element, corner)
-// order starting from +0.0 — the reference's `+=` order into a zeroed matrix (solver.rs:295-323).
-// Returns n, or -1 when the row has more than kFastCols columns (cols / acc are then meaningless).
-template <class Pt>
-MAG_HD int build_row_table(const Conn &m, const Pt *xy, const double *D, double t, const uint32_t *pay,
-                           uint32_t begin, uint32_t end, uint32_t *cols, double *acc) {
-    int n = 0;
-    for (uint32_t i = begin; i < end; ++i) {
-        uint32_t nd[3];
-        corner_nodes(m, pay[i] / 3u, nd);
-        for (int k = 0; k < 3; ++k) {
-            n = insert_col(cols, n, nd[k], kFastCols);
-            if (n < 0) return -1;
-        }
-    }
-    for (int j = 0; j < 4 * n; ++j) acc[j] = 0.0;
-    for (uint32_t i = begin; i < end; ++i) {
-        const uint32_t p = pay[i], le = p / 3u;
-        const int lr = (int)(p - 3u * le);
-        uint32_t nd[3];
-        corner_nodes(m, le, nd);
-        double rows[2][6];
-        ke_rows(xy, nd, lr, D, t, rows);
-        for (int lc = 0; lc < 3; ++lc) {
-            int slot = 0;
-            while (cols[slot] != nd[lc]) ++slot;
-            double *a = acc + 4 * slot;
-            a[0] = gadd(a[0], rows[0][2 * lc]); a[1] = gadd(a[1], rows[0][2 * lc + 1]);
-            a[2] = gadd(a[2], rows[1][2 * lc]); a[3] = gadd(a[3], rows[1][2 * lc + 1]);
-        }
-    }
-    return n;
-}
-
-// The same table from MATERIALISED element matrices: kblk is element_stiffness_kernel's block-major output,
-// kblk[(local_element*9 + lr*3 + lc)*4 + q] = K_e[2lr + q/2][2lc + q%2] — the three blocks an incidence
-// (element, lr) contributes are 96 contiguous bytes.  Same additions in the same order as build_row_table.
-MAG_HD int build_row_table_from_ke(const Conn &m, const double *kblk, const uint32_t *pay, uint32_t begin,
-                                   uint32_t end, uint32_t *cols, double *acc) {
-    int n = 0;
-    for (uint32_t i = begin; i < end; ++i) {
-        uint32_t nd[3];
-        corner_nodes(m, pay[i] / 3u, nd);
-        for (int k = 0; k < 3; ++k) {
-            n = insert_col(cols, n, nd[k], kFastCols);
-            if (n < 0) return -1;
-        }
-    }
-    for (int j = 0; j < 4 * n; ++j) acc[j] = 0.0;
-    for (uint32_t i = begin; i < end; ++i) {
-        const uint32_t p = pay[i];
-        uint32_t nd[3];
-        corner_nodes(m, p / 3u, nd);
-        const double *blk = kblk + (size_t)p * 12;           // (le*9 + lr*3)*4 = (le*3 + lr)*12 = p*12
-        for (int lc = 0; lc < 3; ++lc) {
-            int slot = 0;
-            while (cols[slot] != nd[lc]) ++slot;
-            double *a = acc + 4 * slot;
-            a[0] = gadd(a[0], blk[4 * lc]); a[1] = gadd(a[1], blk[4 * lc + 1]);
-            a[2] = gadd(a[2], blk[4 * lc + 2]); a[3] = gadd(a[3], blk[4 * lc + 3]);
-        }
-    }
-    return n;
 }
 
 // Writes the block row of one node: bcol[0..ncols) ascending column nodes, bval[4*j..4*j+4) the 2x2

@@ -521,18 +521,10 @@ static void post_local(mag_ctx *ctx, mag_system *S, PostBuffers &B, bool want_si
         MAG_LAUNCH(ctx, scatter_solution_kernel, cdiv(N, 256), 256, 0, (const uint8_t *)S->known.p,
                    (const uint32_t *)S->colmap.p, (const double *)S->bc_ux.p, (const double *)S->bc_uy.p,
                    (const double *)B.xfull.p, N, B.ux.p, B.uy.p);
-        const uint32_t n_own = S->K.node_hi - S->K.node_lo, n_owned_dof = 2 * n_own;
-        upload_material(ctx, S->mat);
-        if (n_owned_dof && S->has_K)
+        const uint32_t n_owned_dof = 2 * (S->K.node_hi - S->K.node_lo);
+        if (n_owned_dof)
             MAG_LAUNCH(ctx, reactions_kernel, cdiv(n_owned_dof, 256), 256, 0, (const uint32_t *)S->K.browptr.p,
                        (const uint32_t *)S->K.bcol.p, (const double *)S->K.bval.p, S->K.node_lo, n_owned_dof,
-                       (const uint8_t *)S->known.p, (const double *)S->bc_fx.p, (const double *)S->bc_fy.p,
-                       (const double *)B.ux.p, (const double *)B.uy.p, B.fx.p, B.fy.p);
-        else if (n_own)      // fused assembly: K was never stored; the few rows with an unknown force are rebuilt
-            MAG_LAUNCH(ctx, gather_reactions_kernel, cdiv(n_own, 128), 128, 0, (const double2 *)S->xy.p,
-                       (const uint32_t *)S->n0.p, (const uint32_t *)S->n1.p, (const uint32_t *)S->n2.p,
-                       S->nranks > 1 ? (const uint32_t *)S->elist.p : (const uint32_t *)nullptr,
-                       (const uint32_t *)S->inc.pay.p, (const uint32_t *)S->inc.nptr.p, n_own, S->K.node_lo,
                        (const uint8_t *)S->known.p, (const double *)S->bc_fx.p, (const double *)S->bc_fy.p,
                        (const double *)B.ux.p, (const double *)B.uy.p, B.fx.p, B.fy.p);
     }

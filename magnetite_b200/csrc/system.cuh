@@ -35,12 +35,7 @@ struct mag_system {
     mag::DevBuf<uint32_t> n0, n1, n2;
     mag::DevBuf<uint8_t> known;
     mag::DevBuf<double> bc_ux, bc_uy, bc_fx, bc_fy;
-    mag::BsrMatrix K;                        // full K, owned node rows (assembly modes 1, 2; built on demand for the
-                                             // parity export after the fused assembly, which never stores it)
-    bool has_K = false;
-    mag::Incidence inc;                      // fused assembly: node -> (element, corner) lists, kept for the reactions
-    mag::DevBuf<uint32_t> elist;             // multi-rank: the elements touching an owned node (ascending)
-    size_t n_local_elems = 0;
+    mag::BsrMatrix K;                        // full K, owned node rows
     mag::DevBuf<uint32_t> rowmap, colmap;    // n_dof+1 each (global; last = total)
     mag::DevBuf<uint32_t> colid;             // n_dof: reduced column, or ~0 where the displacement is prescribed
     mag::CsrMatrix Kff;                      // owned rows x global cols
@@ -178,7 +173,87 @@ static void assemble_impl(mag_ctx *ctx, const mag_mesh *m, const mag_material *m
     upload_material(ctx, *mat);
     st.ms_upload = phase.stop();
 
-    // ---- free-DOF maps (solver.rs:340-354, 380-396): needed by every assembly mode -------------------
+    // ---- element stiffness (solver.rs:553-563) for the elements this rank needs ----
+    phase.start();
+    DevBuf<uint32_t> elist;
+    size_t El = E;
+    if (nranks > 1 && E) {
+        DevBuf<uint32_t> flag(ctx, E + 1);
+        MAG_LAUNCH(ctx, flag_elements_kernel, cdiv(E, 256), 256, 0, (const uint32_t *)S->n0.p,
+                   (const uint32_t *)S->n1.p, (const uint32_t *)S->n2.p, E, S->node_lo, S->node_hi, flag.p);
+        exclusive_scan_u32(ctx, flag.p, E, flag.p, E + 1);
+        El = read_u32(ctx, flag.p + E);
+        elist.alloc(ctx, El);
+        MAG_LAUNCH(ctx, compact_elements_kernel, cdiv(E, 256), 256, 0, (const uint32_t *)flag.p, E, elist.p);
+    }
+    if ((uint64_t)El * 9 >= (1ull << 32))
+        fail(MAG_ERR_BAD_ARG, "this rank would assemble %zu elements; 9 COO keys each must stay below 2^32: use more GPUs", El);
+    const uint32_t *elist_p = (nranks > 1) ? elist.p : nullptr;
+    BsrMatrix &K = S->K;
+    K.node_lo = S->node_lo; K.node_hi = S->node_hi;
+    const uint32_t n_own = K.node_hi - K.node_lo;
+    const int asm_mode = opt ? opt->assembly : 0;       // 0 (default) gather, 1 sorted COO keys
+    if (asm_mode < 0 || asm_mode > 1) fail(MAG_ERR_BAD_ARG, "mag_options.assembly must be 0 (gather) or 1 (sorted COO keys)");
+    const bool use_gather = asm_mode == 0;
+    if (use_gather) {
+        // gather assembly (gather.cuh): no K_e in memory, 3E incidences sorted by node instead of 9E COO keys
+        st.ms_elem = phase.stop();                  // only the rank's element list: K_e rows are recomputed in the gather
+        assemble_gather(ctx, S->xy, S->n0, S->n1, S->n2, elist_p, El, N, K, &st.ms_sort, &st.ms_reduce);
+        elist.release();
+    } else {
+        DevBuf<double> kblk(ctx, El * 36);
+        if (El)
+            MAG_LAUNCH(ctx, element_stiffness_kernel, cdiv(El, kElemThreads), kElemThreads, 0,
+                       (const double2 *)S->xy.p, (const uint32_t *)S->n0.p, (const uint32_t *)S->n1.p,
+                       (const uint32_t *)S->n2.p, elist_p, El, 1, kblk.p);
+        st.ms_elem = phase.stop();
+
+        // ---- COO keys + stable sort ----------------------------------------------
+        phase.start();
+        const size_t n_keys = El * 9;
+        const int bits = bits_for(N + 1);
+        DevBuf<uint64_t> keys(ctx, n_keys), keys_alt(ctx, n_keys);
+        DevBuf<uint32_t> pay(ctx, n_keys), pay_alt(ctx, n_keys);
+        if (El) {
+            MAG_LAUNCH(ctx, emit_keys_kernel, cdiv(El, 256), 256, 0, (const uint32_t *)S->n0.p,
+                       (const uint32_t *)S->n1.p, (const uint32_t *)S->n2.p, elist_p, El, bits, S->node_lo,
+                       S->node_hi, keys.p, pay.p);
+            radix_sort_pairs(ctx, keys.p, pay.p, keys_alt.p, pay_alt.p, n_keys, 2 * bits);
+        }
+        keys_alt.release();
+        pay_alt.release();
+        elist.release();
+        st.ms_sort = phase.stop();
+
+        // ---- segmented reduction into BSR ------------------------------------------
+        phase.start();
+        K.browptr.alloc(ctx, (size_t)n_own + 1);
+        K.browptr.zero();
+        {
+            DevBuf<uint32_t> head(ctx, n_keys + 1);
+            if (n_keys)
+                MAG_LAUNCH(ctx, mark_heads_kernel, cdiv(n_keys, 256), 256, 0, (const uint64_t *)keys.p,
+                           n_keys, bits, K.node_lo, head.p, K.browptr.p);
+            DevBuf<uint32_t> uid(ctx, n_keys + 1);      // exclusive scan of head; uid[n_keys] = #blocks
+            exclusive_scan_u32(ctx, head.p, n_keys, uid.p, n_keys + 1);
+            exclusive_scan_u32(ctx, K.browptr.p, n_own, K.browptr.p, (size_t)n_own + 1);
+            K.n_blocks = read_u32(ctx, uid.p + n_keys);
+            K.brow.alloc(ctx, K.n_blocks);
+            K.bcol.alloc(ctx, K.n_blocks);
+            K.bval.alloc(ctx, (size_t)K.n_blocks * 4);
+            if (n_keys)
+                MAG_LAUNCH(ctx, segment_reduce_kernel, cdiv(n_keys, 256), 256, 0, (const uint64_t *)keys.p,
+                           (const uint32_t *)pay.p, (const uint32_t *)head.p, (const uint32_t *)uid.p,
+                           n_keys, bits, K.node_lo, (const double *)kblk.p, K.brow.p, K.bcol.p, K.bval.p);
+        }
+        keys.release();
+        pay.release();
+        kblk.release();
+        st.ms_reduce = phase.stop();
+    }
+    st.nnz_structural = (uint64_t)K.n_blocks * 4;
+
+    // ---- Dirichlet elimination (solver.rs:340-432, 126-137) --------------------
     phase.start();
     S->rowmap.alloc(ctx, n_dof + 1);
     S->colmap.alloc(ctx, n_dof + 1);
@@ -187,17 +262,16 @@ static void assemble_impl(mag_ctx *ctx, const mag_mesh *m, const mag_material *m
     if (n_dof)
         MAG_LAUNCH(ctx, dof_flags_kernel, cdiv(n_dof, 256), 256, 0, (const uint8_t *)S->known.p, n_dof,
                    S->rowmap.p, S->colmap.p, unpaired.p);
-    exclusive_scan_u32(ctx, S->rowmap.p, n_dof, S->rowmap.p, n_dof + 1);
-    exclusive_scan_u32(ctx, S->colmap.p, n_dof, S->colmap.p, n_dof + 1);
-    uint32_t n_rows_glob = 0, n_cols = 0;
     {
         int h_unpaired = 0;
         MAG_CUDA(cudaMemcpyAsync(&h_unpaired, unpaired.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        MAG_CUDA(cudaMemcpyAsync(&n_rows_glob, S->rowmap.p + n_dof, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        MAG_CUDA(cudaMemcpyAsync(&n_cols, S->colmap.p + n_dof, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         MAG_CUDA(cudaStreamSynchronize(ctx->stream));
         S->bc_paired = h_unpaired == 0;
     }
+    exclusive_scan_u32(ctx, S->rowmap.p, n_dof, S->rowmap.p, n_dof + 1);
+    exclusive_scan_u32(ctx, S->colmap.p, n_dof, S->colmap.p, n_dof + 1);
+    const uint32_t n_rows_glob = read_u32(ctx, S->rowmap.p + n_dof);
+    const uint32_t n_cols = read_u32(ctx, S->colmap.p + n_dof);
     if (n_rows_glob != n_cols)
         fail(MAG_ERR_BAD_BC,
              "inconsistent boundary conditions: %u DOFs have a known force but %u have an unknown "
@@ -211,30 +285,6 @@ static void assemble_impl(mag_ctx *ctx, const mag_mesh *m, const mag_material *m
                                          : read_u32(ctx, S->rowmap.p + 2 * (size_t)S->all_node_lo[r]);
     S->row_lo = S->all_row_lo[rank]; S->row_hi = S->all_row_lo[rank + 1];
     const uint32_t n_rows = S->row_hi - S->row_lo;
-    float ms_maps = phase.stop();
-
-    // ---- the elements this rank needs (multi-rank: those touching an owned node) ----------------------
-    phase.start();
-    DevBuf<uint32_t> &elist = S->elist;
-    size_t El = E;
-    if (nranks > 1 && E) {
-        DevBuf<uint32_t> flag(ctx, E + 1);
-        MAG_LAUNCH(ctx, flag_elements_kernel, cdiv(E, 256), 256, 0, (const uint32_t *)S->n0.p,
-                   (const uint32_t *)S->n1.p, (const uint32_t *)S->n2.p, E, S->node_lo, S->node_hi, flag.p);
-        exclusive_scan_u32(ctx, flag.p, E, flag.p, E + 1);
-        El = read_u32(ctx, flag.p + E);
-        elist.alloc(ctx, El);
-        MAG_LAUNCH(ctx, compact_elements_kernel, cdiv(E, 256), 256, 0, (const uint32_t *)flag.p, E, elist.p);
-    }
-    S->n_local_elems = El;
-    if ((uint64_t)El * 9 >= (1ull << 32))
-        fail(MAG_ERR_BAD_ARG, "this rank would assemble %zu elements; 9 COO keys each must stay below 2^32: use more GPUs", El);
-    const uint32_t *elist_p = (nranks > 1) ? elist.p : nullptr;
-    BsrMatrix &K = S->K;
-    K.node_lo = S->node_lo; K.node_hi = S->node_hi;
-    const uint32_t n_own = K.node_hi - K.node_lo;
-    const int asm_mode = opt ? opt->assembly : 0;       // 0 fused gather (default), 1 gather -> BSR -> eliminate, 2 sorted COO keys
-    if (asm_mode < 0 || asm_mode > 2) fail(MAG_ERR_BAD_ARG, "mag_options.assembly must be 0, 1 or 2");
     CsrMatrix &A = S->Kff;
     A.n_rows = n_rows; A.row_lo = S->row_lo; A.n_cols = n_cols;
     A.rowptr.alloc(ctx, (size_t)n_rows + 1);
@@ -242,163 +292,27 @@ static void assemble_impl(mag_ctx *ctx, const mag_mesh *m, const mag_material *m
     S->diag.alloc(ctx, n_rows);
     const int drop = opt ? opt->drop_exact_zeros : 1;
     const uint32_t n_owned_dof = 2 * n_own;
-
-    if (asm_mode == 0) {
-        // ---- fused gather (gather.cuh): K_e per triangle, incidence lists, row tables in shared memory -> K_ff
-        DevBuf<double> kblk(ctx, El * 36);
-        if (El)
-            MAG_LAUNCH(ctx, element_stiffness_kernel, cdiv(El, kElemThreads), kElemThreads, 0,
-                       (const double2 *)S->xy.p, (const uint32_t *)S->n0.p, (const uint32_t *)S->n1.p,
-                       (const uint32_t *)S->n2.p, elist_p, El, 1, kblk.p);
-        st.ms_elem = phase.stop();
-        phase.start();
-        build_incidence(ctx, S->n0, S->n1, S->n2, elist_p, El, N, S->node_lo, S->node_hi, S->inc);
-        st.ms_sort = phase.stop();
-
-        phase.start();
-        S->colid.alloc(ctx, n_dof + 2);
-        if (n_dof)
-            MAG_LAUNCH(ctx, col_ids_kernel, cdiv(n_dof, 256), 256, 0, (const uint8_t *)S->known.p,
-                       (const uint32_t *)S->colmap.p, n_dof, S->colid.p);
-        S->diag.zero();                             // the fill pass writes the diagonal where it keeps one
-        const ElimView EV{S->known.p, S->rowmap.p, S->colmap.p, reinterpret_cast<const uint2 *>(S->colid.p),
-                          S->bc_ux.p, S->bc_uy.p, S->bc_fx.p, S->bc_fy.p, drop, A.row_lo, S->node_lo};
-        DevBuf<unsigned long long> counters(ctx, 2);            // [0] structural blocks, [1] nnz (one-pass kernel)
-        counters.zero();
-        A.rowptr.zero();
-        unsigned long long h_counters[2] = {0, 0};
-        if (ctx->tune & 64) {
-            // MAG_TUNE=64: two passes (count -> scan -> fill) instead of the one-pass kernel (comparison / fallback)
-            launch_fused_rows<0>(ctx, S->xy, S->n0, S->n1, S->n2, elist_p, kblk.p, S->inc, n_own, EV, A.rowptr.p, nullptr,
-                                 nullptr, nullptr, nullptr, nullptr, counters.p);
-            exclusive_scan_u32(ctx, A.rowptr.p, n_rows, A.rowptr.p, (size_t)n_rows + 1);
-            uint32_t h_nnz = 0;
-            MAG_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-            MAG_CUDA(cudaMemcpyAsync(&h_nnz, A.rowptr.p + n_rows, sizeof h_nnz, cudaMemcpyDeviceToHost, ctx->stream));
-            MAG_CUDA(cudaStreamSynchronize(ctx->stream));
-            A.nnz = h_nnz;
-            st.ms_reduce = phase.stop();
-            phase.start();
-            A.col.alloc(ctx, A.nnz);
-            A.val.alloc(ctx, A.nnz);
-            launch_fused_rows<1>(ctx, S->xy, S->n0, S->n1, S->n2, elist_p, kblk.p, S->inc, n_own, EV, nullptr,
-                                 (const uint32_t *)A.rowptr.p, A.col.p, A.val.p, S->rhs.p, S->diag.p, nullptr);
-        } else {
-            // one pass: the tiles find their place in the CSR arrays by decoupled look-back.  Capacity: a node with d
-            // incident triangles has at most 2d + 1 column nodes, so K_ff has at most 4 * (2 * 3 * El + n_own) entries;
-            // the arrays are cut back to nnz afterwards.
-            const size_t cap = 4 * (6 * (size_t)El + (size_t)n_own);
-            if (cap >= (1ull << 32)) fail(MAG_ERR_BAD_ARG, "this rank's K_ff could reach %zu entries; the CSR offsets are 32-bit: use more GPUs", cap);
-            A.col.alloc(ctx, cap);
-            A.val.alloc(ctx, cap);
-            const unsigned tiles = cdiv(n_own, kFusedThreads);
-            DevBuf<unsigned long long> status(ctx, (size_t)tiles + 1);
-            DevBuf<unsigned> ticket(ctx, 1);
-            DevBuf<int> err(ctx, 1);
-            status.zero(); ticket.zero(); err.zero();
-            if (n_own) {
-                ensure_fused_attrs(ctx);
-                const TileScan T{status.p, ticket.p, counters.p + 1, err.p};
-                MAG_LAUNCH(ctx, fused_rows_onepass_kernel, tiles, kFusedThreads, kFusedSmem, (const double2 *)S->xy.p,
-                           (const uint32_t *)S->n0.p, (const uint32_t *)S->n1.p, (const uint32_t *)S->n2.p, elist_p,
-                           (const double *)kblk.p, (const uint32_t *)S->inc.pay.p, (const uint32_t *)S->inc.nptr.p, n_own,
-                           n_rows, EV, A.rowptr.p, A.col.p, A.val.p, S->rhs.p, S->diag.p, counters.p, T);
-            }
-            int h_err = 0;
-            MAG_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof h_counters, cudaMemcpyDeviceToHost, ctx->stream));
-            MAG_CUDA(cudaMemcpyAsync(&h_err, err.p, sizeof h_err, cudaMemcpyDeviceToHost, ctx->stream));
-            MAG_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (h_err) fail(MAG_ERR_CUDA, "fused assembly: a tile never published its row count (look-back guard tripped)");
-            A.nnz = h_counters[1];
-            A.col.shrink(A.nnz);
-            A.val.shrink(A.nnz);
-            st.ms_reduce = 0.f;
-        }
-        K.n_blocks = (uint32_t)h_counters[0];       // structural size only: the block rows themselves are not stored
-        S->has_K = false;
-    } else {
-        if (asm_mode == 1) {
-            // gather assembly with the block rows materialised (gather.cuh): no K_e in memory, 3E incidences sorted
-            st.ms_elem = phase.stop();
-            phase.start();
-            build_incidence(ctx, S->n0, S->n1, S->n2, elist_p, El, N, S->node_lo, S->node_hi, S->inc);
-            st.ms_sort = phase.stop();
-            phase.start();
-            build_bsr_from_incidence(ctx, S->xy, S->n0, S->n1, S->n2, elist_p, S->inc, K);
-            st.ms_reduce = phase.stop();
-        } else {
-            // ---- element stiffness (solver.rs:553-563) -------------------------------------------
-            DevBuf<double> kblk(ctx, El * 36);
-            if (El)
-                MAG_LAUNCH(ctx, element_stiffness_kernel, cdiv(El, kElemThreads), kElemThreads, 0,
-                           (const double2 *)S->xy.p, (const uint32_t *)S->n0.p, (const uint32_t *)S->n1.p,
-                           (const uint32_t *)S->n2.p, elist_p, El, 1, kblk.p);
-            st.ms_elem = phase.stop();
-
-            // ---- COO keys + stable sort ----------------------------------------------
-            phase.start();
-            const size_t n_keys = El * 9;
-            const int bits = bits_for(N + 1);
-            DevBuf<uint64_t> keys(ctx, n_keys), keys_alt(ctx, n_keys);
-            DevBuf<uint32_t> pay(ctx, n_keys), pay_alt(ctx, n_keys);
-            if (El) {
-                MAG_LAUNCH(ctx, emit_keys_kernel, cdiv(El, 256), 256, 0, (const uint32_t *)S->n0.p,
-                           (const uint32_t *)S->n1.p, (const uint32_t *)S->n2.p, elist_p, El, bits, S->node_lo,
-                           S->node_hi, keys.p, pay.p);
-                radix_sort_pairs(ctx, keys.p, pay.p, keys_alt.p, pay_alt.p, n_keys, 2 * bits);
-            }
-            keys_alt.release();
-            pay_alt.release();
-            st.ms_sort = phase.stop();
-
-            // ---- segmented reduction into BSR ------------------------------------------
-            phase.start();
-            K.browptr.alloc(ctx, (size_t)n_own + 1);
-            K.browptr.zero();
-            {
-                DevBuf<uint32_t> head(ctx, n_keys + 1);
-                if (n_keys)
-                    MAG_LAUNCH(ctx, mark_heads_kernel, cdiv(n_keys, 256), 256, 0, (const uint64_t *)keys.p,
-                               n_keys, bits, K.node_lo, head.p, K.browptr.p);
-                DevBuf<uint32_t> uid(ctx, n_keys + 1);      // exclusive scan of head; uid[n_keys] = #blocks
-                exclusive_scan_u32(ctx, head.p, n_keys, uid.p, n_keys + 1);
-                exclusive_scan_u32(ctx, K.browptr.p, n_own, K.browptr.p, (size_t)n_own + 1);
-                K.n_blocks = read_u32(ctx, uid.p + n_keys);
-                K.bcol.alloc(ctx, K.n_blocks);
-                K.bval.alloc(ctx, (size_t)K.n_blocks * 4);
-                if (n_keys)
-                    MAG_LAUNCH(ctx, segment_reduce_kernel, cdiv(n_keys, 256), 256, 0, (const uint64_t *)keys.p,
-                               (const uint32_t *)pay.p, (const uint32_t *)head.p, (const uint32_t *)uid.p,
-                               n_keys, bits, (const double *)kblk.p, K.bcol.p, K.bval.p);
-            }
-            st.ms_reduce = phase.stop();
-        }
-        S->has_K = true;
-
-        // ---- Dirichlet elimination (solver.rs:340-432, 126-137) --------------------
-        phase.start();
-        if (n_owned_dof)
-            MAG_LAUNCH(ctx, eliminate_kernel<0>, cdiv(n_owned_dof, 256), 256, 0,
-                       (const uint32_t *)K.browptr.p, (const uint32_t *)K.bcol.p, (const double *)K.bval.p,
-                       K.node_lo, n_owned_dof, (const uint8_t *)S->known.p, (const uint32_t *)S->rowmap.p,
-                       (const uint32_t *)S->colmap.p, (const double *)S->bc_ux.p, (const double *)S->bc_uy.p,
-                       (const double *)S->bc_fx.p, (const double *)S->bc_fy.p, drop, A.row_lo,
-                       A.rowptr.p, (const uint32_t *)nullptr, (int32_t *)nullptr, (double *)nullptr,
-                       (double *)nullptr, (double *)nullptr);
-        exclusive_scan_u32(ctx, A.rowptr.p, n_rows, A.rowptr.p, (size_t)n_rows + 1);
-        A.nnz = read_u32(ctx, A.rowptr.p + n_rows);
-        A.col.alloc(ctx, A.nnz);
-        A.val.alloc(ctx, A.nnz);
-        if (n_owned_dof)
-            MAG_LAUNCH(ctx, eliminate_kernel<1>, cdiv(n_owned_dof, 256), 256, 0,
-                       (const uint32_t *)K.browptr.p, (const uint32_t *)K.bcol.p, (const double *)K.bval.p,
-                       K.node_lo, n_owned_dof, (const uint8_t *)S->known.p, (const uint32_t *)S->rowmap.p,
-                       (const uint32_t *)S->colmap.p, (const double *)S->bc_ux.p, (const double *)S->bc_uy.p,
-                       (const double *)S->bc_fx.p, (const double *)S->bc_fy.p, drop, A.row_lo,
-                       (uint32_t *)nullptr, (const uint32_t *)A.rowptr.p, A.col.p, A.val.p, S->rhs.p,
-                       S->diag.p);
-    }
-    st.nnz_structural = (uint64_t)K.n_blocks * 4;
+    S->colid.alloc(ctx, n_dof + 2);
+    if (n_dof)
+        MAG_LAUNCH(ctx, col_ids_kernel, cdiv(n_dof, 256), 256, 0, (const uint8_t *)S->known.p,
+                   (const uint32_t *)S->colmap.p, n_dof, S->colid.p);
+    const uint2 *colid2 = reinterpret_cast<const uint2 *>(S->colid.p);
+    A.rowptr.zero();
+    if (n_owned_dof)
+        MAG_LAUNCH(ctx, eliminate_rows_kernel, cdiv(n_owned_dof, 256), 256, 0,
+                   (const uint32_t *)K.browptr.p, (const uint32_t *)K.bcol.p, (const double *)K.bval.p,
+                   K.node_lo, n_owned_dof, (const uint8_t *)S->known.p, (const uint32_t *)S->rowmap.p, colid2,
+                   (const double *)S->bc_ux.p, (const double *)S->bc_uy.p, (const double *)S->bc_fx.p,
+                   (const double *)S->bc_fy.p, drop, A.row_lo, A.rowptr.p, S->rhs.p, S->diag.p);
+    exclusive_scan_u32(ctx, A.rowptr.p, n_rows, A.rowptr.p, (size_t)n_rows + 1);
+    A.nnz = read_u32(ctx, A.rowptr.p + n_rows);
+    A.col.alloc(ctx, A.nnz);
+    A.val.alloc(ctx, A.nnz);
+    if (K.n_blocks)
+        MAG_LAUNCH(ctx, eliminate_fill_blocks_kernel, cdiv(K.n_blocks, 256), 256, 0,
+                   (const uint32_t *)K.browptr.p, (const uint32_t *)K.brow.p, (const uint32_t *)K.bcol.p,
+                   (const double *)K.bval.p, K.n_blocks, K.node_lo, (const uint8_t *)S->known.p,
+                   (const uint32_t *)S->rowmap.p, colid2, drop, A.row_lo, (const uint32_t *)A.rowptr.p, A.col.p, A.val.p);
     st.nnz = A.nnz;
     // halo extent: the columns the owned rows touch
     S->ext_lo = S->row_lo; S->ext_hi = S->row_hi;
@@ -414,7 +328,7 @@ static void assemble_impl(mag_ctx *ctx, const mag_mesh *m, const mag_material *m
         S->ext_lo = std::min<uint32_t>(S->row_lo, (uint32_t)h[0]);
         S->ext_hi = std::max<uint32_t>(S->row_hi, (uint32_t)h[1] + 1);
     }
-    st.ms_bc = phase.stop() + ms_maps;
+    st.ms_bc = phase.stop();
 
     // ---- solver format -------------------------------------------------------------
     phase.start();

@@ -1,6 +1,6 @@
-"""The three assembly modes of mag_options.assembly on the device-resident plate — 0 fused gather (default),
-1 gather into block rows + elimination kernels, 2 sorted COO keys + segmented reduction + elimination kernels:
-    python profiles/assembly_probe.py [nx ny reps [modes]]   (default 4000 2000 3 012 = 16 M DOF, all modes)
+"""The two assembly modes of mag_options.assembly on the device-resident plate — 0 gather (default), 1 sorted COO
+keys + segmented reduction; both followed by the same elimination kernels:
+    python profiles/assembly_probe.py [nx ny reps [modes]]   (default 4000 2000 3 01 = 16 M DOF, both modes)
 
 Prints the library's phase timers (CUDA events on its stream) for every repetition and checks at full size
 that all paths leave the same K_ff: same counts, and the order-preserving CSR SpMV of the systems on one
@@ -20,8 +20,8 @@ PHASES = ("ms_upload", "ms_elem", "ms_sort", "ms_reduce", "ms_bc", "ms_format", 
 
 def main():
     nx, ny, reps = (int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (4000, 2000, 3)
-    modes = [int(c) for c in (sys.argv[4] if len(sys.argv) > 4 else "012")]
-    names = {0: "fused gather", 1: "gather + eliminate", 2: "sorted keys"}
+    modes = [int(c) for c in (sys.argv[4] if len(sys.argv) > 4 else "01")]
+    names = {0: "gather", 1: "sorted keys"}
     lib = _lib.load()
     ctx = _lib.Context(0)
     mat = solver._material(meshgen.EXAMPLE_MATERIAL)

@@ -41,8 +41,8 @@ def material():
 @pytest.fixture(scope="session", autouse=True)
 def _assembly_override():
     """MAGNETITE_B200_TEST_ASSEMBLY=1 runs every test that builds its options through the Python binding with the
-    gather assembly (mag_options.assembly = 1) unless the test sets the field itself: the whole parity suite
-    against the opt-in path with one command.  Unset (the default) nothing changes."""
+    sorted-key assembly (mag_options.assembly = 1) unless the test sets the field itself: the whole parity suite
+    against the non-default path with one command.  Unset (the default) nothing changes."""
     import os
     want = os.environ.get("MAGNETITE_B200_TEST_ASSEMBLY")
     if want is None:

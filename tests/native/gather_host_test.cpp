@@ -13,10 +13,7 @@
 
 namespace {
 struct P2 { double x, y; };
-int g_mode = 0;      // 0: fill_row (gather_fill_kernel's core); 1: build_row_table / for_each_block_serial (fused kernels' cores)
 }
-
-extern "C" void gather_host_set_mode(int mode) { g_mode = mode; }
 
 // Returns the number of 2x2 blocks of the node rows [node_lo, node_hi).  browptr (n_own + 1) is always
 // written; bcol / bval only when capacity_blocks is large enough.
@@ -56,27 +53,8 @@ extern "C" uint64_t gather_host_assemble(uint64_t n_nodes, uint64_t n_elems, con
         browptr[r + 1] = browptr[r] + count_cols(conn, sorted.data(), nptr[r], nptr[r + 1]);
     const uint64_t n_blocks = browptr[n_own];
     if (n_blocks > capacity_blocks || !bcol || !bval) return n_blocks;
-    for (uint32_t r = 0; r < n_own; ++r) {
-        uint32_t *bc = bcol + browptr[r];
-        double *bv = bval + 4 * (size_t)browptr[r];
-        if (g_mode == 0) {                                    // gather_fill_kernel
-            fill_row(conn, xy.data(), D9, t, sorted.data(), nptr[r], nptr[r + 1], browptr[r + 1] - browptr[r], bc, bv);
-            continue;
-        }
-        uint32_t cols[kFastCols];                             // fused_rows_kernel: table, else the serial traversal
-        double acc[kFastCols * 4];
-        const int n = build_row_table(conn, xy.data(), D9, t, sorted.data(), nptr[r], nptr[r + 1], cols, acc);
-        if (n >= 0) {
-            if ((uint32_t)n != browptr[r + 1] - browptr[r]) return ~0ull;
-            for (int j = 0; j < n; ++j) { bc[j] = cols[j]; for (int q = 0; q < 4; ++q) bv[4 * j + q] = acc[4 * j + q]; }
-        } else {
-            uint32_t j = 0;
-            for_each_block_serial(conn, xy.data(), D9, t, sorted.data(), nptr[r], nptr[r + 1],
-                                  [&](uint32_t c, double a0, double a1, double a2, double a3) {
-                bc[j] = c; bv[4 * j] = a0; bv[4 * j + 1] = a1; bv[4 * j + 2] = a2; bv[4 * j + 3] = a3; ++j;
-            });
-            if (j != browptr[r + 1] - browptr[r]) return ~0ull;
-        }
-    }
+    for (uint32_t r = 0; r < n_own; ++r)                      // gather_fill_kernel
+        fill_row(conn, xy.data(), D9, t, sorted.data(), nptr[r], nptr[r + 1], browptr[r + 1] - browptr[r],
+                 bcol + browptr[r], bval + 4 * (size_t)browptr[r]);
     return n_blocks;
 }

@@ -2,7 +2,7 @@
 CUDA kernels of gather.cuh call, compiled here by g++ into a test harness, tests/native/gather_host_test.cpp):
 the block rows it produces equal the oracle's full K (solver.rs:290-331) bit for bit, on every mesh family
 the GPU parity tests use, for whole meshes and for the node ranges of a 3-way partition.  The kernels'
-launch glue itself is covered by tests/test_gpu_parity.py (`assembly=1`)."""
+launch glue itself is covered by tests/test_gpu_parity.py (default mode, `assembly=0`)."""
 import ctypes as C
 import subprocess
 from pathlib import Path
@@ -31,7 +31,6 @@ def harness(built):
     lib = C.CDLL(str(out))
     vp = C.c_void_p
     lib.gather_host_assemble.restype = C.c_uint64
-    lib.gather_host_set_mode.argtypes = [C.c_int]
     lib.gather_host_assemble.argtypes = [C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, vp, C.c_double, C.c_uint32,
                                          C.c_uint32, C.c_int, vp, vp, vp, C.c_uint64]
     return lib
@@ -121,20 +120,14 @@ MESHES = {
     "fan_40": _fan,
     "fan_17": lambda: _fan(17),             # 18 columns in the hub row: just past kMaxCols
     "fan_15": lambda: _fan(15),             # 16 columns: the last size the thread-local path takes
-    "fan_10": lambda: _fan(10),             # 11 columns: the last size the shared-memory row table takes
-    "fan_11": lambda: _fan(11),             # 12 columns: the first row of the table-free traversal
     "degenerate": _degenerate,
     "example_linkedin": lambda: _example("example_linkedin"),      # Delaunay mesh in gmsh-like order
     "example_tensile": lambda: _example("example_tensile"),        # all clockwise after check_ccw
 }
 
 
-@pytest.mark.parametrize("core", ["fill_row", "row_table"])
 @pytest.mark.parametrize("name", list(MESHES))
-def test_gather_core_matches_the_oracle_bit_for_bit(harness, name, core):
-    # fill_row: the core of gather_fill_kernel (assembly = 1); row_table: build_row_table (<= kFastCols = 11 columns)
-    # and for_each_block_serial beyond, the cores of the fused default assembly and of the reaction rows
-    harness.gather_host_set_mode(0 if core == "fill_row" else 1)
+def test_gather_core_matches_the_oracle_bit_for_bit(harness, name):
     mesh = MESHES[name]()
     n = mesh.n_nodes
     want = _oracle_rows(mesh, META, 0, n)
@@ -146,7 +139,6 @@ def test_gather_core_matches_the_oracle_bit_for_bit(harness, name, core):
 
 
 def test_gather_core_edge_cases(harness):
-    harness.gather_host_set_mode(0)
     empty = MeshSoA(*(np.zeros(0, t) for t in (np.float64, np.float64, np.uint32, np.uint32, np.uint32, np.float64,
                                                  np.float64, np.float64, np.float64, np.uint8)))
     rp, col, val = _gather_rows(harness, empty, META, 0, 0, False)
