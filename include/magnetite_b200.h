@@ -80,7 +80,8 @@ typedef struct {
     double rel_tol;          /* stop at ||r||_2 <= rel_tol*||b||_2   (default 1e-9)   */
     double abs_tol;          /* compat target cost                   (default 1e-4)   */
     uint64_t max_iter;       /* default 1e7                                            */
-    int32_t precond;         /* 0 none, 1 Jacobi (default), 2 Jacobi + aggregation coarse space */
+    int32_t precond;         /* 0 none, 1 Jacobi, 2 Jacobi + aggregation coarse space (falls back to Jacobi when the
+                              * system is not SPD), 3 (default) auto: 2 for systems of >= 20 000 unknowns, else 1 */
     int32_t compat;          /* 1: reference semantics — plain CG, x0=0, absolute cost */
     int32_t cost_kind;       /* compat cost: 0 = ||r||_2 (default), 1 = r.r            */
     int32_t drop_exact_zeros;/* 1 (default): K_ff keeps k != 0.0 only (solver.rs:132)  */
@@ -130,7 +131,7 @@ typedef struct {
     float ms_coarse_setup;             /* precond 2: building P, Ac and Ac^-1 (inside ms_solve, first solve only) */
     uint32_t n_coarse;                 /* precond 2: coarse unknowns (3 per aggregate)                            */
     uint32_t sell_index_bits;          /* 16: column offsets from the row (band < 32768), 32: absolute columns    */
-    uint32_t reserved;
+    uint32_t precond_used;             /* what the solve ran with: 0 plain CG, 1 Jacobi, 2 two-level             */
 } mag_stats;
 
 typedef struct mag_ctx mag_ctx;        /* device + stream + memory pool + comm    */

@@ -65,7 +65,7 @@ class MagStats(C.Structure):
                 ("ms_total", C.c_float), ("kernel_launches", C.c_uint64),
                 ("spmv_bytes", C.c_uint64), ("prof", C.c_double * 8),
                 ("ms_coarse_setup", C.c_float), ("n_coarse", C.c_uint32),
-                ("sell_index_bits", C.c_uint32), ("reserved", C.c_uint32)]
+                ("sell_index_bits", C.c_uint32), ("precond_used", C.c_uint32)]
 
     def as_dict(self) -> dict:
         d = {name: getattr(self, name) for name, _ in self._fields_}

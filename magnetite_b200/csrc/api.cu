@@ -92,7 +92,7 @@ extern "C" int mag_ctx_create(mag_ctx **out, int device) {
         c->sm_count = prop.multiProcessorCount;
         MAG_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
         c->stream = c->own_stream;
-        MAG_CUDA(cudaMallocHost((void **)&c->h_scal, 64 * sizeof(double)));
+        MAG_CUDA(cudaMallocHost((void **)&c->h_scal, 128 * sizeof(double)));
         if (const char *t = std::getenv("MAG_TUNE")) c->tune = std::atoi(t);
         *out = c.release();
     });
@@ -106,7 +106,6 @@ extern "C" void mag_ctx_destroy(mag_ctx *ctx) {
         if (ctx->comm->nccl) ncclCommDestroy(ctx->comm->nccl);
         delete ctx->comm;
     }
-    if (ctx->cusolver) cusolver_api().destroy(ctx->cusolver);
     ctx->heap.destroy();
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -119,7 +118,7 @@ extern "C" void mag_options_default(mag_options *o) {
     o->rel_tol = 1e-9;
     o->abs_tol = MAG_TARGET_CG_COST;
     o->max_iter = MAG_MAX_CG_ITER;
-    o->precond = 1;
+    o->precond = 3;
     o->compat = 0;
     o->cost_kind = 0;
     o->drop_exact_zeros = 1;

@@ -90,7 +90,6 @@ struct mag_ctx {
     bool rs_attr_set = false;           // radix sort (64-bit keys): dynamic shared memory opt-in done on this device
     bool rs32_attr_set = false;         // same, 32-bit keys
     bool fused_attr_set = false;        // fused assembly kernels: dynamic shared memory opt-in
-    void *cusolver = nullptr;           // cusolverDnHandle_t, created on first use of the two-level preconditioner
     mag::Comm *comm = nullptr;
     // pinned host scratch for scalar read-backs
     double *h_scal = nullptr;

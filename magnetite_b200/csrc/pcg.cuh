@@ -54,6 +54,7 @@ struct PcgScalars {
     double wy;           // two-level preconditioner: (P^T r).(Ac^-1 P^T r), the coarse part of r.z
     double loc_pair[2];  // this rank's partial sums (send buffers of the NCCL fallback)
     double loc_pq;
+    double loc_wy;       // this rank's share of w.y (NCCL / emulated reductions)
     double thr2;         // stop when r.r <= thr2
     double first_pq;     // its sign tells negative-definite systems
     unsigned long long iter, max_iter;
@@ -129,7 +130,7 @@ __device__ __forceinline__ uint32_t ll_seq(const PcgScalars *sc, unsigned long l
 
 // ---- allreduce over peer memory: mailboxes ----------------------------------------
 constexpr int kMaxRanks = 16;
-enum { kMailPq = 0, kMailPair = 1, kMailInit = 2, kMailKinds = 3 };
+enum { kMailPq = 0, kMailPair = 1, kMailInit = 2, kMailWy = 3, kMailKinds = 4 };
 struct MailSlot { LLWord w[2]; };
 constexpr int kMailSlots = kMailKinds * 2 * kMaxRanks;     // [kind][parity][src]
 struct PeerLinks {
@@ -319,7 +320,13 @@ pcg_update_p_kernel(double *__restrict__ p, const double *__restrict__ r,
         rz_new = g.x; rr = g.y;
     }
     const double g_rz = rz_new;
-    if (cv.mode) rz_new += sc->wy;          // r.z = r.Dinv r + (P^T r).(Ac^-1 P^T r)
+    if (cv.mode) {                          // r.z = r.Dinv r + (P^T r).(Ac^-1 P^T r)
+        double wy = sc->wy;
+        if (links.n) {                      // every rank's share of w.y, added in rank order
+            wy = mailbox_gather(links, kMailWy, parity, seq, sc, -1).x;
+        }
+        rz_new += wy;
+    }
     const double rz_old = sc->rzc[parity], pq = sc->pq;
     const bool use_halo = halo.ll != nullptr && !(sc->tune & 1);
     // One thread moves the iteration on.  Nothing another CTA of this launch still reads is
@@ -394,9 +401,11 @@ pcg_init_p_kernel(double *__restrict__ p, const double *__restrict__ r, const do
     const uint32_t seq = ll_seq(sc, 0);
     if (links.n) {
         const double2 g = mailbox_gather(links, kMailInit, 0, seq, sc, -1);
+        double wy = 0.0;
+        if (cv.mode) wy = mailbox_gather(links, kMailWy, 0, seq, sc, -1).x;
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             sc->pair[0][0] = g.x; sc->pair[0][1] = g.y;
-            sc->rzc[0] = g.x + (cv.mode ? sc->wy : 0.0);
+            sc->rzc[0] = g.x + wy;
         }
         __threadfence_system();        // acquire side of the Dinv halo
     } else if (blockIdx.x == 0 && threadIdx.x == 0) {

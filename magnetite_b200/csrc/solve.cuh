@@ -28,16 +28,18 @@ inline size_t ext_len(const mag_system *S) { return (((size_t)S->n_free + 32) + 
 inline size_t halo_count(const mag_system *S) {
     return (size_t)(S->row_lo - S->ext_lo) + (size_t)(S->ext_hi - S->row_hi);
 }
-// Slab other ranks store into: [ Dinv (global-indexed) | mailbox | halo buffer of r (LL words) ]
+// Slab other ranks store into: [ Dinv (global-indexed) | mailbox | coarse w partials | halo buffer of r (LL words) ]
 inline size_t slab_bytes(const mag_system *S) {
-    return ext_len(S) * sizeof(double) + kMailSlots * sizeof(MailSlot) + (halo_count(S) + 1) * sizeof(LLWord);
+    return ext_len(S) * sizeof(double) + kMailSlots * sizeof(MailSlot) + kCoarseWbufWords * sizeof(LLWord) +
+           (halo_count(S) + 1) * sizeof(LLWord);
 }
 inline MailSlot *slab_mailbox(const mag_system *S, double *slab) {
     return reinterpret_cast<MailSlot *>(slab + ext_len(S));
 }
-inline LLWord *slab_halo(const mag_system *S, double *slab) {
+inline LLWord *slab_wbuf(const mag_system *S, double *slab) {
     return reinterpret_cast<LLWord *>(slab_mailbox(S, slab) + kMailSlots);
 }
+inline LLWord *slab_halo(const mag_system *S, double *slab) { return slab_wbuf(S, slab) + kCoarseWbufWords; }
 
 // Plain cudaMalloc so it can be exported through CUDA IPC.  Mailbox and halo buffer start
 // zeroed and are never reset afterwards (sequence numbers only move forward).
@@ -86,6 +88,10 @@ static void build_push_segments(mag_system *S, const std::vector<uint32_t> &ext_
         ps.dinv_dst[ps.n] = peer_slab[g.dst];
         ++ps.n;
     }
+    // where the partial restrictions of the two-level preconditioner go: every rank's buffer
+    CoarseLinks &cl = S->coarse.links;
+    cl.n = S->nranks; cl.me = S->rank;
+    for (int r = 0; r < S->nranks; ++r) cl.wbuf[r] = slab_wbuf(S, peer_slab[r]);
     S->push_ready = true;
 }
 
@@ -148,6 +154,8 @@ constexpr size_t kOffPq = offsetof(PcgScalars, pq) / sizeof(double);
 constexpr size_t kOffLocPair = offsetof(PcgScalars, loc_pair) / sizeof(double);
 constexpr size_t kOffLocPq = offsetof(PcgScalars, loc_pq) / sizeof(double);
 
+constexpr uint32_t kAutoTwoLevelMinRows = 20000;    // precond 3: below this Jacobi-PCG is faster than the coarse setup
+
 struct SolveMode {
     Reduce reduce = Reduce::kNone;
     int format = 2;
@@ -206,23 +214,29 @@ static void reduce_vector(mag_ctx *ctx, std::vector<RankState> &ranks, const Sol
     (void)m;
 }
 
-// w = P^T r (per rank) -> sum over ranks -> y = Ac^-1 w and wy = w.y (every rank, redundantly)
-static void enqueue_coarse_solve(mag_ctx *ctx, std::vector<RankState> &ranks, const SolveMode &m) {
-    std::vector<double *> ws;
+constexpr size_t kOffWy = offsetof(PcgScalars, wy) / sizeof(double);
+constexpr size_t kOffLocWy = offsetof(PcgScalars, loc_wy) / sizeof(double);
+
+// w = P^T r (per rank, straight into every rank's buffer) -> y = (this rank's rows of Ac^-1) w and its share of w.y
+// step < 0: the initial residual.
+static void enqueue_coarse_solve(mag_ctx *ctx, std::vector<RankState> &ranks, const SolveMode &m, int step) {
     for (RankState &W : ranks) {
         CoarseSpace &C = W.S->coarse;
-        MAG_LAUNCH(ctx, coarse_restrict_kernel, C.n_agg, kRestrictThreads, 0, (const uint32_t *)C.agg_ptr.p,
-                   (const uint32_t *)C.perm.p, (const uint32_t *)C.mode.p, (const double *)C.rot.p,
-                   (const double *)W.r_ext, W.S->row_lo, C.w.p, (const PcgScalars *)W.scal.p);
-        ws.push_back(C.w.p);
+        if (C.n_lagg)
+            MAG_LAUNCH(ctx, coarse_restrict_kernel, C.n_lagg, kRestrictThreads, 0, (const uint32_t *)C.lagg.p,
+                       (const uint32_t *)C.agg_ptr.p, (const uint32_t *)C.perm_ax.p, (const double *)C.rot_perm.p,
+                       (const double *)W.r_ext, W.S->row_lo, step, C.links, (const PcgScalars *)W.scal.p);
     }
-    reduce_vector(ctx, ranks, m, ws, ranks[0].S->coarse.nc);
+    const bool local_sum = m.reduce == Reduce::kNccl || m.reduce == Reduce::kEmulated;
     for (RankState &W : ranks) {
         CoarseSpace &C = W.S->coarse;
-        const unsigned grid = std::max(1u, std::min(cdiv((size_t)C.nc * 32, 256), (unsigned)ctx->sm_count * 8u));
-        MAG_LAUNCH(ctx, coarse_gemv_kernel, grid, 256, 0, (const double *)C.Ainv.p, (const double *)C.w.p, C.y.p,
-                   C.nc, C.partials.p, C.ticket.p, W.scal.p, scal_field(W, offsetof(PcgScalars, wy) / sizeof(double)));
+        const unsigned grid = std::max(1u, std::min(cdiv((size_t)C.m * 32, 256), (unsigned)ctx->sm_count * 2u));
+        MAG_LAUNCH(ctx, coarse_apply_kernel, grid, 256, (size_t)C.nc * sizeof(double), (const double *)C.Ainv.p,
+                   (const uint32_t *)C.crow.p, (const uint8_t *)C.wy_mine.p, (const uint16_t *)C.touch.p, C.m, C.nc, step,
+                   C.links, links_of(W, m), C.y.p, C.partials.p, C.ticket.p, W.scal.p,
+                   scal_field(W, local_sum ? kOffLocWy : kOffWy));
     }
+    reduce_scalars(ctx, ranks, m, kOffLocWy, kOffWy, 1);
 }
 
 static void enqueue_iteration(mag_ctx *ctx, std::vector<RankState> &ranks, int step, const SolveMode &m) {
@@ -249,15 +263,33 @@ static void enqueue_iteration(mag_ctx *ctx, std::vector<RankState> &ranks, int s
                    (const double *)W.q.p, (const double *)W.dinv_ext, W.n, W.S->row_lo, step, W.S->push,
                    links_of(W, m), W.partials.p, W.scal.p, pair_target(W, m, parity ^ 1));
     reduce_scalars(ctx, ranks, m, kOffLocPair, kOffPair0 + 2 * (size_t)(parity ^ 1), 2);
-    if (m.two_level) enqueue_coarse_solve(ctx, ranks, m);
+    if (m.two_level) enqueue_coarse_solve(ctx, ranks, m, step);
     for (RankState &W : ranks)
         MAG_LAUNCH(ctx, pcg_update_p_kernel, W.grid_ext, 256, 0, W.p_ext.p, (const double *)W.r_ext,
                    (const double *)W.dinv_ext, W.S->ext_lo, W.S->ext_hi, step, W.halo, coarse_view(W, m),
                    links_of(W, m), W.scal.p);
 }
 
-// Builds the aggregation coarse space of every rank's system (once per system).
-static void setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const SolveMode &m, const mag_options &opt) {
+// Small host-side exchanges of the setup: one byte string per rank -> all of them on every rank.
+static std::vector<std::vector<uint8_t>> exchange_bytes(mag_ctx *ctx, std::vector<RankState> &ranks,
+                                                         const std::vector<std::vector<uint8_t>> &mine, size_t bytes) {
+    const int R = ranks.size() > 1 ? (int)ranks.size() : ranks[0].S->nranks;
+    std::vector<std::vector<uint8_t>> all(R);
+    if (ranks.size() > 1) {
+        for (int r = 0; r < R; ++r) all[r] = mine[r];
+    } else if (R == 1) {
+        all[0] = mine[0];
+    } else {
+        std::vector<uint8_t> flat((size_t)R * bytes);
+        allgather_bytes(ctx, mine[0].data(), bytes, flat.data());
+        for (int r = 0; r < R; ++r) all[r].assign(flat.begin() + (size_t)r * bytes, flat.begin() + (size_t)(r + 1) * bytes);
+    }
+    return all;
+}
+
+// Builds the aggregation coarse space of every rank's system (once per system).  Returns false when Ac is not
+// positive definite (the system is not SPD, e.g. an all-clockwise mesh): the caller falls back to Jacobi.
+static bool setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const SolveMode &m, const mag_options &opt) {
     const bool trace = (ctx->tune & 32) != 0;          // MAG_TUNE=32: wall-clock of the setup stages on stderr
     auto t_last = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) {
@@ -267,11 +299,15 @@ static void setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
         std::fprintf(stderr, "[coarse setup] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
         t_last = now;
     };
-    bool all_ready = true;
-    for (RankState &W : ranks) all_ready = all_ready && W.S->coarse.ready;
-    if (all_ready) return;
+    bool all_ready = true, any_failed = false;
+    for (RankState &W : ranks) { all_ready = all_ready && W.S->coarse.ready; any_failed = any_failed || W.S->coarse.failed; }
+    if (any_failed) return false;
+    if (all_ready) return true;
+    const int R = ranks.size() > 1 ? (int)ranks.size() : ranks[0].S->nranks;
     std::vector<double *> mats;
-    for (RankState &W : ranks) {
+    std::vector<std::vector<uint8_t>> has_rows(ranks.size()), need(ranks.size());
+    for (size_t q = 0; q < ranks.size(); ++q) {
+        RankState &W = ranks[q];
         mag_system *S = W.S;
         CoarseSpace &C = S->coarse;
         const size_t N = S->n_nodes, n_dof = 2 * N;
@@ -289,50 +325,78 @@ static void setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
         }
         const double Wd = std::max(xmax - xmin, 1e-300), Hd = std::max(ymax - ymin, 1e-300);
         uint32_t target = opt.coarse_aggregates > 0 ? (uint32_t)opt.coarse_aggregates
-                                                    : (uint32_t)std::min<uint64_t>(2048, std::max<uint64_t>(4, S->n_free / 4096));
-        target = std::min(target, 2048u);
-        C.nbx = std::max(1u, (uint32_t)std::lround(std::sqrt((double)target * Wd / Hd)));
-        C.nby = std::max(1u, (uint32_t)std::lround((double)target / C.nbx));
-        C.n_agg = C.nbx * C.nby;
+                                                    : (uint32_t)std::min<uint64_t>(kCoarseMaxAgg, std::max<uint64_t>(4, S->n_free / 4096));
+        target = std::min(target, kCoarseMaxAgg);
+        CoarseGrid &g = C.grid;
+        g.nbx = std::max(1u, (uint32_t)std::lround(std::sqrt((double)target * Wd / Hd)));
+        g.nby = std::max(1u, (uint32_t)std::lround((double)target / g.nbx));
+        while ((uint64_t)g.nbx * g.nby > kCoarseMaxAgg) { if (g.nbx >= g.nby) --g.nbx; else --g.nby; }
+        g.x_fast = g.nbx <= g.nby ? 1 : 0;          // number along the shorter side: narrow band
+        g.x0 = xmin; g.y0 = ymin;
+        g.hx = Wd / g.nbx * (1.0 + 1e-12); g.hy = Hd / g.nby * (1.0 + 1e-12);
+        C.n_agg = g.nbx * g.nby;
         C.nc = 3 * C.n_agg;
-        C.x0 = xmin; C.y0 = ymin;
-        C.hx = Wd / C.nbx * (1.0 + 1e-12); C.hy = Hd / C.nby * (1.0 + 1e-12);
+        C.hb = std::min(C.nc - 1, 3 * (std::min(g.nbx, g.nby) + 1) + 2);
         lap("bounding box");
         C.mode.alloc(ctx, ext_len(S)); C.rot.alloc(ctx, ext_len(S));
         C.mode.zero(); C.rot.zero();
         MAG_LAUNCH(ctx, coarse_colinfo_kernel, cdiv(n_dof, 256), 256, 0, (const double2 *)S->xy.p,
-                   (const uint8_t *)S->known.p, (const uint32_t *)S->colmap.p, n_dof, C.x0, C.y0, C.hx, C.hy,
-                   C.nbx, C.nby, C.mode.p, C.rot.p);
+                   (const uint8_t *)S->known.p, (const uint32_t *)S->colmap.p, n_dof, g, C.mode.p, C.rot.p);
         lap("column info");
         // local rows sorted by aggregate
         const uint32_t n = S->Kff.n_rows;
-        C.perm.alloc(ctx, n);
+        C.perm_ax.alloc(ctx, n); C.rot_perm.alloc(ctx, n);
         C.agg_ptr.alloc(ctx, (size_t)C.n_agg + 1);
         {
             DevBuf<uint64_t> keys(ctx, n), keys_alt(ctx, n);
-            DevBuf<uint32_t> pay_alt(ctx, n);
+            DevBuf<uint32_t> perm(ctx, n), pay_alt(ctx, n);
             if (n) {
                 MAG_LAUNCH(ctx, coarse_rowkeys_kernel, cdiv(n, 256), 256, 0, (const uint32_t *)C.mode.p, n, S->row_lo,
-                           keys.p, C.perm.p);
-                radix_sort_pairs(ctx, keys.p, C.perm.p, keys_alt.p, pay_alt.p, n, bits_for((uint64_t)C.n_agg + 1));
+                           keys.p, perm.p);
+                radix_sort_pairs(ctx, keys.p, perm.p, keys_alt.p, pay_alt.p, n, bits_for((uint64_t)C.n_agg + 1));
+                MAG_LAUNCH(ctx, coarse_pack_rows_kernel, cdiv(n, 256), 256, 0, (const uint32_t *)perm.p,
+                           (const uint32_t *)C.mode.p, (const double *)C.rot.p, n, S->row_lo, C.perm_ax.p, C.rot_perm.p);
             }
             MAG_LAUNCH(ctx, coarse_segments_kernel, cdiv((size_t)C.n_agg + 1, 256), 256, 0, (const uint64_t *)keys.p, n,
                        C.n_agg, C.agg_ptr.p);
         }
         lap("sort rows by aggregate");
+        // which aggregates have rows of this rank, and which ones its rows and halo touch
+        std::vector<uint32_t> h_ptr((size_t)C.n_agg + 1);
+        DevBuf<uint8_t> d_need(ctx, C.n_agg);
+        d_need.zero();
+        if (S->ext_hi > S->ext_lo)
+            MAG_LAUNCH(ctx, coarse_needed_kernel, cdiv(S->ext_hi - S->ext_lo, 256), 256, 0, (const uint32_t *)C.mode.p,
+                       S->ext_lo, S->ext_hi, d_need.p);
+        need[q].resize(C.n_agg);
+        MAG_CUDA(cudaMemcpyAsync(h_ptr.data(), C.agg_ptr.p, h_ptr.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        MAG_CUDA(cudaMemcpyAsync(need[q].data(), d_need.p, C.n_agg, cudaMemcpyDeviceToHost, ctx->stream));
+        MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+        has_rows[q].resize(C.n_agg);
+        std::vector<uint32_t> h_lagg;
+        for (uint32_t a = 0; a < C.n_agg; ++a) {
+            has_rows[q][a] = h_ptr[a + 1] > h_ptr[a] ? 1 : 0;
+            if (has_rows[q][a]) h_lagg.push_back(a);
+        }
+        C.n_lagg = (uint32_t)h_lagg.size();
+        C.lagg.alloc(ctx, h_lagg.size());
+        if (!h_lagg.empty())
+            MAG_CUDA(cudaMemcpyAsync(C.lagg.p, h_lagg.data(), h_lagg.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        MAG_CUDA(cudaStreamSynchronize(ctx->stream));
         // Galerkin product of the local rows
         C.Ac_compact.alloc(ctx, (size_t)C.n_agg * 81);
         DevBuf<int> far(ctx, 1);
         far.zero();
-        MAG_LAUNCH(ctx, coarse_galerkin_kernel, C.n_agg, 96, 0, (const uint32_t *)C.agg_ptr.p, (const uint32_t *)C.perm.p,
+        MAG_LAUNCH(ctx, coarse_galerkin_kernel, C.n_agg, 96, 0, (const uint32_t *)C.agg_ptr.p, (const uint32_t *)C.perm_ax.p,
                    (const uint32_t *)S->Kff.rowptr.p, (const int32_t *)S->Kff.col.p, (const double *)S->Kff.val.p,
-                   (const uint32_t *)C.mode.p, (const double *)C.rot.p, S->row_lo, C.nbx, C.nby, C.nc, C.Ac_compact.p, far.p);
+                   (const uint32_t *)C.mode.p, (const double *)C.rot.p, S->row_lo, g, C.Ac_compact.p, far.p);
         int h_far = 0;
         MAG_CUDA(cudaMemcpyAsync(&h_far, far.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         MAG_CUDA(cudaStreamSynchronize(ctx->stream));
         if (h_far) fail(MAG_ERR_BAD_ARG, "two-level preconditioner: an element spans non-adjacent aggregates "
-                                          "(%u x %u boxes are too small for this mesh); lower coarse_aggregates", C.nbx, C.nby);
-        C.w.alloc(ctx, C.nc); C.y.alloc(ctx, C.nc);
+                                          "(%u x %u boxes are too small for this mesh); lower coarse_aggregates", g.nbx, g.nby);
+        C.y.alloc(ctx, C.nc);
+        C.y.zero();
         C.partials.alloc(ctx, 2 * (size_t)ctx->sm_count * 8);
         C.ticket.alloc(ctx, 1);
         C.ticket.zero();
@@ -341,17 +405,77 @@ static void setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
     }
     reduce_vector(ctx, ranks, m, mats, (size_t)ranks[0].S->coarse.n_agg * 81);      // block rows, summed over ranks
     lap("sum over ranks");
-    for (RankState &W : ranks) {
-        CoarseSpace &C = W.S->coarse;
-        C.Ainv.alloc(ctx, (size_t)C.nc * C.nc);
-        C.Ainv.zero();
-        MAG_LAUNCH(ctx, coarse_expand_kernel, C.n_agg, 96, 0, (const double *)C.Ac_compact.p, C.nbx, C.nby, C.nc, C.Ainv.p);
+    const uint32_t n_agg = ranks[0].S->coarse.n_agg;
+    const std::vector<std::vector<uint8_t>> all_has = exchange_bytes(ctx, ranks, has_rows, n_agg);
+    std::vector<uint16_t> touch(n_agg, 0);
+    for (uint32_t a = 0; a < n_agg; ++a)
+        for (int r = 0; r < R; ++r)
+            if (all_has[r][a]) touch[a] |= (uint16_t)(1u << r);
+    bool spd = true;
+    for (size_t q = 0; q < ranks.size(); ++q) {
+        RankState &W = ranks[q];
+        mag_system *S = W.S;
+        CoarseSpace &C = S->coarse;
+        const int me = S->rank;
+        const uint32_t nc = C.nc, hb = C.hb, Wb = hb + 1;
+        // the rows of Ac^-1 this rank applies: 3 per aggregate its rows or halo touch; w.y is added by the lowest
+        // rank that has rows in the aggregate
+        std::vector<uint32_t> h_crow;
+        std::vector<uint8_t> h_mine;
+        for (uint32_t a = 0; a < n_agg; ++a) {
+            if (!need[q][a] && !all_has[me][a]) continue;
+            const bool mine = touch[a] != 0 && (touch[a] & (uint16_t)((1u << me) - 1u)) == 0 && ((touch[a] >> me) & 1u);
+            for (uint32_t j = 0; j < 3; ++j) { h_crow.push_back(3 * a + j); h_mine.push_back(mine ? 1 : 0); }
+        }
+        C.m = (uint32_t)h_crow.size();
+        C.crow.alloc(ctx, C.m); C.wy_mine.alloc(ctx, C.m); C.touch.alloc(ctx, n_agg);
+        if (C.m) {
+            MAG_CUDA(cudaMemcpyAsync(C.crow.p, h_crow.data(), (size_t)C.m * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+            MAG_CUDA(cudaMemcpyAsync(C.wy_mine.p, h_mine.data(), C.m, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        MAG_CUDA(cudaMemcpyAsync(C.touch.p, touch.data(), (size_t)n_agg * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+        MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+        // banded Cholesky of Ac (every rank, ~2 ms), then only this rank's rows of the inverse
+        DevBuf<double> lower(ctx, (size_t)nc * Wb), upper(ctx, (size_t)nc * Wb), invd(ctx, nc);
+        DevBuf<int> bad(ctx, 1);
+        lower.zero(); bad.zero();
+        MAG_LAUNCH(ctx, coarse_band_kernel, C.n_agg, 96, 0, (const double *)C.Ac_compact.p, C.grid, hb, lower.p);
         C.Ac_compact.release();
-        MAG_LAUNCH(ctx, coarse_fix_diagonal_kernel, cdiv(C.nc, 256), 256, 0, C.Ainv.p, C.nc);
-        spd_inverse(ctx, C.Ainv.p, C.nc);
+        MAG_LAUNCH(ctx, coarse_fix_diagonal_kernel, cdiv(nc, 256), 256, 0, lower.p, nc, hb);
+        const size_t chol_smem = ((size_t)Wb * Wb + Wb) * sizeof(double);
+        if (chol_smem > 200 * 1024) fail(MAG_ERR_BAD_ARG, "two-level preconditioner: band of %u does not fit the factorisation window", hb);
+        MAG_CUDA(cudaFuncSetAttribute(band_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
+        MAG_LAUNCH(ctx, band_cholesky_kernel, 1, 1024, chol_smem, lower.p, nc, hb, invd.p, bad.p);
+        int h_bad = 0;
+        MAG_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+        lap("banded Cholesky");
+        if (h_bad) { spd = false; C.failed = true; continue; }
+        MAG_LAUNCH(ctx, band_transpose_kernel, cdiv((size_t)nc * Wb, 256), 256, 0, (const double *)lower.p, nc, hb, upper.p);
+        C.Ainv.alloc(ctx, (size_t)std::max(C.m, 1u) * nc);
+        if (C.m) {
+            const size_t inv_smem = ((size_t)kInvChunk + kInvWarps) * Wb * sizeof(double);
+            MAG_CUDA(cudaFuncSetAttribute(band_inverse_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem));
+            MAG_LAUNCH(ctx, band_inverse_rows_kernel, cdiv(C.m, kInvWarps), kInvWarps * 32, inv_smem, (const double *)lower.p,
+                       (const double *)upper.p, (const double *)invd.p, nc, hb, (const uint32_t *)C.crow.p, C.m, C.Ainv.p);
+        }
+        MAG_CUDA(cudaFuncSetAttribute(coarse_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCoarseMax * sizeof(double))));
+        // single rank without a shared slab: its own buffer for the partial restrictions
+        if (!S->shared_slab) {
+            C.wbuf_local.alloc(ctx, kCoarseWbufWords);
+            C.wbuf_local.zero();
+            C.links.n = 1; C.links.me = 0;
+            C.links.wbuf[0] = C.wbuf_local.p;
+        }
+        MAG_CUDA(cudaStreamSynchronize(ctx->stream));
         C.ready = true;
-        lap("expand + potrf + potri");
+        lap("rows of the inverse");
     }
+    if (!spd) {
+        for (RankState &W : ranks) { W.S->coarse.failed = true; W.S->coarse.ready = false; }
+        return false;
+    }
+    return true;
 }
 
 struct SolveOutcome {
@@ -359,6 +483,7 @@ struct SolveOutcome {
     double bb = 0.0;
     float ms_coarse_setup = 0.f;
     uint32_t n_coarse = 0;
+    int precond_used = 0;
     bool rerun_best = false;
 };
 
@@ -370,7 +495,9 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
     else if (ranks[0].S->nranks > 1) mode.reduce = opt.allreduce == 1 ? Reduce::kNccl : Reduce::kMailbox;
     const bool compat = opt.compat != 0;
     const int jacobi = compat ? 0 : (opt.precond != 0);
-    mode.two_level = !compat && opt.precond == 2;
+    // precond 3 (the default): two-level when the system is large enough to pay for the setup and turns out SPD
+    const bool want_two = !compat && (opt.precond == 2 || (opt.precond == 3 && ranks[0].S->n_free >= kAutoTwoLevelMinRows));
+    mode.two_level = want_two;
     int chunk = opt.check_every > 0 ? opt.check_every : 50;
     chunk += chunk & 1;   // iteration parity is baked into the graph: even chunk length
     SolveOutcome out;
@@ -381,10 +508,11 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
     if (mode.two_level) {
         EventTimer t(ctx->stream);
         t.start();
-        setup_coarse(ctx, ranks, mode, opt);
+        mode.two_level = setup_coarse(ctx, ranks, mode, opt);      // false: Ac not positive definite -> Jacobi
         out.ms_coarse_setup = t.stop();
-        out.n_coarse = ranks[0].S->coarse.nc;
+        out.n_coarse = mode.two_level ? ranks[0].S->coarse.nc : 0;
     }
+    out.precond_used = compat ? 0 : (mode.two_level ? 2 : (jacobi ? 1 : 0));
 
     for (RankState &W : ranks) {
         PcgScalars z;
@@ -399,7 +527,7 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
                    W.S->push, links_of(W, mode), W.partials.p, W.scal.p, pair_target(W, mode, 0));
     // the reduction also orders the halo stores of r and Dinv before their readers
     reduce_scalars(ctx, ranks, mode, kOffLocPair, kOffPair0, 2);
-    if (mode.two_level) enqueue_coarse_solve(ctx, ranks, mode);
+    if (mode.two_level) enqueue_coarse_solve(ctx, ranks, mode, -1);
     for (RankState &W : ranks)
         MAG_LAUNCH(ctx, pcg_init_p_kernel, W.grid_ext, 256, 0, W.p_ext.p, (const double *)W.r_ext,
                    (const double *)W.dinv_ext, W.S->ext_lo, W.S->ext_hi, W.halo, coarse_view(W, mode),
@@ -445,7 +573,7 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
     const uint64_t per_chunk = ctx->launches - l0;
     ctx->launches = l0;
     MAG_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-    static_assert(2 * sizeof(PcgScalars) <= 64 * sizeof(double), "pinned scratch too small");
+    static_assert(2 * sizeof(PcgScalars) <= 128 * sizeof(double), "pinned scratch too small");
     PcgScalars *slot[2] = {reinterpret_cast<PcgScalars *>(ctx->h_scal),
                            reinterpret_cast<PcgScalars *>(ctx->h_scal) + 1};
     cudaEvent_t ev[2];
@@ -505,6 +633,7 @@ static void fill_solve_stats(mag_stats &st, const SolveOutcome &o, uint32_t n_gl
     st.converged = (hs.stop == 1) || n_glob == 0;
     st.ms_coarse_setup = o.ms_coarse_setup;
     st.n_coarse = o.n_coarse;
+    st.precond_used = (uint32_t)o.precond_used;
     for (int i = 0; i < 8; ++i) st.prof[i] = hs.prof[7] > 0 && i < 7 ? hs.prof[i] / hs.prof[7] : hs.prof[i];
     st.negative_definite = hs.first_pq < 0.0;
 }

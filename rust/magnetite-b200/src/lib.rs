@@ -72,7 +72,7 @@ pub mod sys {
         pub ms_format: f32, pub ms_solve: f32, pub ms_post: f32, pub ms_download: f32, pub ms_total: f32,
         pub kernel_launches: u64, pub spmv_bytes: u64,
         pub prof: [f64; 8],
-        pub ms_coarse_setup: f32, pub n_coarse: u32, pub sell_index_bits: u32, pub reserved: u32,
+        pub ms_coarse_setup: f32, pub n_coarse: u32, pub sell_index_bits: u32, pub precond_used: u32,
     }
     pub enum mag_ctx {}
 

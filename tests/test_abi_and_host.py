@@ -40,7 +40,7 @@ def test_struct_layouts_match_header(built):
     assert C.sizeof(_lib.MagOptions) == 8 + 8 + 8 + 10 * 4 + 8
     assert C.sizeof(_lib.MagResult) == 6 * 8 + 8
     o = _lib.default_options()
-    assert (o.rel_tol, o.abs_tol, o.max_iter, o.precond, o.compat, o.drop_exact_zeros) == (1e-9, 1e-4, 10_000_000, 1, 0, 1)
+    assert (o.rel_tol, o.abs_tol, o.max_iter, o.precond, o.compat, o.drop_exact_zeros) == (1e-9, 1e-4, 10_000_000, 3, 0, 1)
 
 
 def test_no_cpu_fallback(built):

@@ -455,10 +455,16 @@ def test_two_level_on_examples_and_indefinite_meshes(ctx):
     meta = META.__class__(*g["material"])
     two = solver.solve_soa(mesh, meta, ctx, _lib.default_options(rel_tol=1e-13, precond=2))
     assert rel_l2(np.concatenate([two.ux, two.uy]), np.concatenate([g["ux"], g["uy"]])) < 1e-9
-    t = np.load(GOLDEN / "example_tensile.npz")            # all-clockwise mesh: negative definite
-    with pytest.raises(MagnetiteError) as ei:
-        solver.solve_soa(golden_mesh(t), META.__class__(*t["material"]), ctx, _lib.default_options(precond=2))
-    assert ei.value.code == _lib.MAG_ERR_INDEFINITE
+    assert two.stats["precond_used"] == 2
+    # all-clockwise mesh: K is negative definite, the coarse matrix has no Cholesky factor: Jacobi takes over
+    t = np.load(GOLDEN / "example_tensile.npz")
+    fb = solver.solve_soa(golden_mesh(t), META.__class__(*t["material"]), ctx, _lib.default_options(rel_tol=1e-13, precond=2))
+    assert fb.stats["precond_used"] == 1 and fb.stats["converged"] == 1 and fb.stats["negative_definite"] == 1
+    assert rel_l2(np.concatenate([fb.ux, fb.uy]), np.concatenate([t["ux"], t["uy"]])) < 1e-9
+    # the default (precond 3 = auto): Jacobi below 20 000 unknowns, two-level above
+    small = solver.solve_soa(meshgen.plate(40, 20), META, ctx, _lib.default_options())
+    large = solver.solve_soa(meshgen.plate(160, 80), META, ctx, _lib.default_options())
+    assert small.stats["precond_used"] == 1 and large.stats["precond_used"] == 2
 
 
 def test_narrow_and_wide_sell_index_streams_agree(ctx):
