@@ -82,6 +82,7 @@ struct CoarseSpace {
     DevBuf<double> Ac_compact;    // n_agg x 81 (setup only)
     DevBuf<double> Ainv;          // m x nc
     DevBuf<double> y;             // nc (entries listed in crow are valid)
+    DevBuf<double> w;             // nc: the complete restriction P^T r
     DevBuf<LLWord> wbuf_local;    // single rank without a shared slab
     DevBuf<double> partials;
     DevBuf<unsigned> ticket;
@@ -174,47 +175,76 @@ __global__ void coarse_needed_kernel(const uint32_t *__restrict__ mode, uint32_t
     if (i < ext_hi) need[mode[i] / 3u] = 1;
 }
 
-// Galerkin product: CTA = aggregate I; thread t < 81 owns entry (neighbour k, alpha, beta) of the 3x27
-// block row and walks the aggregate's rows and their CSR entries in a fixed order.  `far` counts
-// couplings outside the 3x3 neighbourhood (boxes smaller than an element): the caller then refuses.
-__global__ void __launch_bounds__(96)
+// Galerkin product Ac = P^T (K_ff P) for the local rows: CTA = aggregate I, warp w takes the aggregate's rows
+// w, w+8, ... one at a time.  Lane (k, beta) < 27 forms t = (K P)[row][neighbour box k, mode beta] from the row's
+// entries (each lane loads one entry, the entries are broadcast with shuffles in CSR order) and adds
+// P[row][alpha] * t to its three sums (alpha = the row's axis, and the rotation mode).  A fixed assignment of
+// rows to warps, a fixed order inside a warp and a fixed order over the warps: the same bits in every run.
+// `far` reports couplings outside the 3x3 neighbourhood (boxes smaller than an element): the caller refuses.
+constexpr int kGalerkinWarps = 8;
+__global__ void __launch_bounds__(kGalerkinWarps * 32)
 coarse_galerkin_kernel(const uint32_t *__restrict__ agg_ptr, const uint32_t *__restrict__ perm_ax,
                        const uint32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                        const double *__restrict__ val, const uint32_t *__restrict__ mode,
                        const double *__restrict__ rot, uint32_t row_lo, CoarseGrid g,
                        double *__restrict__ Ac, int *__restrict__ far) {
+    __shared__ double part[kGalerkinWarps][81];
     const uint32_t I = blockIdx.x;
-    const int t = threadIdx.x;
-    const int k = t / 9, alpha = (t % 9) / 3, beta = t % 3;
-    uint32_t J = 0xffffffffu;
-    const bool live = t < 81 && g.neighbour(I, k, J);
-    if (!live) J = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k = lane / 3, beta = lane % 3;                     // lanes 27..31 only load entries
     int bx, by;
     g.coords(I, bx, by);
-    double acc = 0.0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;                         // alpha = x-translation, y-translation, rotation
     int far_local = 0;
-    for (uint32_t s = agg_ptr[I]; s < agg_ptr[I + 1]; ++s) {
-        const uint32_t i = perm_ax[s] >> 2;
-        const int axi = (int)(perm_ax[s] & 3u);
-        const double pia = (alpha == axi) ? 1.0 : (alpha == 2 ? rot[row_lo + i] : 0.0);
-        for (uint32_t e = rowptr[i]; e < rowptr[i + 1]; ++e) {
-            const uint32_t c = (uint32_t)col[e];
-            const uint32_t mj = mode[c];
-            const uint32_t aj = mj / 3u;
-            if (t == 0) {
+    for (uint32_t s = agg_ptr[I] + warp; s < agg_ptr[I + 1]; s += kGalerkinWarps) {
+        const uint32_t pa = perm_ax[s], i = pa >> 2;
+        const int axi = (int)(pa & 3u);
+        const double roti = rot[row_lo + i];
+        const uint32_t e0 = rowptr[i], e1 = rowptr[i + 1];
+        double t = 0.0;
+        for (uint32_t base = e0; base < e1; base += 32) {
+            const uint32_t e = base + lane;
+            int kk = -1, axj = 0;
+            double v = 0.0, rc = 0.0;
+            if (e < e1) {
+                const uint32_t c = (uint32_t)col[e];
+                const uint32_t mj = mode[c];
+                v = val[e]; rc = rot[c];
+                axj = (int)(mj % 3u);
                 int cx, cy;
-                g.coords(aj, cx, cy);
-                if (cx - bx < -1 || cx - bx > 1 || cy - by < -1 || cy - by > 1) far_local = 1;
+                g.coords(mj / 3u, cx, cy);
+                const int dx = cx - bx, dy = cy - by;
+                if (dx < -1 || dx > 1 || dy < -1 || dy > 1) far_local = 1;
+                else kk = (dy + 1) * 3 + (dx + 1);
             }
-            if (aj != J || pia == 0.0) continue;
-            const int axj = (int)(mj % 3u);
-            const double pjb = (beta == axj) ? 1.0 : (beta == 2 ? rot[c] : 0.0);
-            acc = fma(pia * val[e], pjb, acc);
+            const int cnt = (int)min(32u, e1 - base);
+            for (int q = 0; q < cnt; ++q) {
+                const int kq = __shfl_sync(0xffffffffu, kk, q), aq = __shfl_sync(0xffffffffu, axj, q);
+                const double vq = __shfl_sync(0xffffffffu, v, q), rq = __shfl_sync(0xffffffffu, rc, q);
+                if (kq == k) {
+                    if (beta == aq) t += vq;
+                    else if (beta == 2) t = fma(vq, rq, t);
+                }
+            }
         }
+        if (axi == 0) a0 += t; else a1 += t;
+        a2 = fma(roti, t, a2);
     }
-    // compact block row: Ac[I][k][alpha][beta], 81 doubles per aggregate (what is summed over the ranks)
-    if (t < 81) Ac[(size_t)I * 81 + t] = live ? acc : 0.0;
-    if (t == 0 && far_local) *far = 1;
+    if (lane < 27) {
+        part[warp][k * 9 + 0 * 3 + beta] = a0;
+        part[warp][k * 9 + 1 * 3 + beta] = a1;
+        part[warp][k * 9 + 2 * 3 + beta] = a2;
+    }
+    if (far_local) *far = 1;
+    __syncthreads();
+    // compact block row: Ac[I][k][alpha][beta], 81 doubles per aggregate (what is summed over the ranks);
+    // neighbours outside the grid never receive anything and stay zero
+    if (threadIdx.x < 81) {
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < kGalerkinWarps; ++q) sum += part[q][threadIdx.x];
+        Ac[(size_t)I * 81 + threadIdx.x] = sum;
+    }
 }
 
 // Lower band of Ac, row-wise: band[row*(hb+1) + k] = Ac[row][row-k], k = 0..hb, from the compact block rows.
@@ -238,51 +268,66 @@ __global__ void coarse_fix_diagonal_kernel(double *__restrict__ band, uint32_t n
 
 // In-place banded Cholesky Ac = L L^T (right-looking), one CTA.  The rows j..j+hb that step j touches sit in a
 // circular shared-memory window win[(row % W)*W + k] = A[row][row-k], W = hb+1; row j leaves for global memory
-// when it is final and row j+W takes its slot.  *not_spd is set at the first non-positive pivot.
+// when it is final and row j+W takes its slot (loaded into registers at the start of the step, so its latency
+// hides behind the step).  Two barriers per step.  *not_spd is set at the first non-positive pivot.
 __global__ void __launch_bounds__(1024)
 band_cholesky_kernel(double *__restrict__ band, uint32_t n, uint32_t hb, double *__restrict__ invd,
                      int *__restrict__ not_spd) {
     extern __shared__ double chol_smem[];
     const uint32_t W = hb + 1;
-    double *win = chol_smem;                 // W*W
+    double *win = chol_smem;                    // W*W
     double *colv = chol_smem + (size_t)W * W;   // W: column j below the diagonal, scaled
-    __shared__ double s_d;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t tx = tid & 31u, ty = tid >> 5;                    // 32 x 32 threads for the trailing update
     for (uint32_t e = tid; e < W * W; e += nt) {
         const uint32_t row = e / W, k = e % W;
         win[e] = row < n ? band[(size_t)row * W + k] : 0.0;
     }
     __syncthreads();
-    for (uint32_t j = 0; j < n; ++j) {
-        double *rowj = win + (size_t)(j % W) * W;
-        if (tid == 0) {
-            double d = rowj[0];
-            if (!(d > 0.0)) { *not_spd = 1; d = 1.0; }
-            d = sqrt(d);
-            rowj[0] = d;
-            s_d = d;
-            invd[j] = 1.0 / d;
-        }
-        __syncthreads();
-        const double d = s_d;
-        const uint32_t pmax = min(hb, n - 1 - j);            // rows j+1 .. j+pmax hold column j
+    uint32_t slot_j = 0;                                             // j % W
+    for (uint32_t j = 0; j < n; ++j, slot_j = (slot_j + 1 == W) ? 0u : slot_j + 1) {
+        double *rowj = win + (size_t)slot_j * W;
+        // the row that enters the window after this step: on its way while the step runs (W <= 1024 threads)
+        double incoming = 0.0;
+        if (tid < W && j + W < n) incoming = band[(size_t)(j + W) * W + tid];
+        double d = rowj[0];                                          // every thread: the same pivot, the same bits
+        if (!(d > 0.0)) { if (tid == 0) *not_spd = 1; d = 1.0; }
+        const double rd = rsqrt(d);                                  // 1/sqrt(pivot); L[j][j] = pivot * rd
+        d *= rd;
+        const uint32_t pmax = min(hb, n - 1 - j);                    // rows j+1 .. j+pmax hold column j
         for (uint32_t p = 1 + tid; p <= pmax; p += nt) {
-            double *ri = win + (size_t)((j + p) % W) * W;
-            const double l = ri[p] / d;
+            uint32_t slot = slot_j + p;
+            if (slot >= W) slot -= W;
+            double *ri = win + (size_t)slot * W;
+            const double l = ri[p] * rd;
             ri[p] = l;
             colv[p] = l;
         }
         __syncthreads();
-        // trailing update: A[j+p][j+q] -= l_p * l_q for 1 <= q <= p <= pmax
-        for (uint32_t e = tid; e < pmax * pmax; e += nt) {
-            const uint32_t p = e / pmax + 1, q = e % pmax + 1;
-            if (q <= p) win[(size_t)((j + p) % W) * W + (p - q)] -= colv[p] * colv[q];
+        // row j is final (its diagonal is d, the rest was finished by earlier steps): store it and put row j+W into
+        // its slot — nothing below touches that slot before the barrier at the end of the step
+        if (tid == 0) invd[j] = rd;
+        if (tid < W) {
+            band[(size_t)j * W + tid] = tid ? rowj[tid] : d;
+            rowj[tid] = incoming;
         }
-        __syncthreads();
-        // row j is final: store it, and bring row j+W into its slot
-        for (uint32_t k = tid; k < W; k += nt) {
-            band[(size_t)j * W + k] = rowj[k];
-            rowj[k] = (j + W < n) ? band[(size_t)(j + W) * W + k] : 0.0;
+        // trailing update: A[j+p][j+q] -= l_p * l_q for 1 <= q <= p <= pmax, in 32 x 32 tiles of (p, q)
+        // (the step is bound by shared-memory traffic: the l_q a thread needs are the same for all its p — registers)
+        double lq[5];
+#pragma unroll
+        for (int u = 0; u < 5; ++u) { const uint32_t q = tx + 1 + 32u * u; lq[u] = q <= pmax ? colv[q] : 0.0; }
+        for (uint32_t p0 = 0; p0 < pmax; p0 += 32) {
+            const uint32_t p = p0 + ty + 1;
+            if (p > pmax) break;
+            uint32_t slot = slot_j + p;
+            if (slot >= W) slot -= W;
+            double *rp = win + (size_t)slot * W;
+            const double lp = colv[p];
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+                const uint32_t q = tx + 1 + 32u * u;
+                if (q <= p) rp[p - q] -= lp * lq[u];
+            }
         }
         __syncthreads();
     }
@@ -299,78 +344,129 @@ __global__ void band_transpose_kernel(const double *__restrict__ lower, uint32_t
 }
 
 // Rows of Ac^-1: out[r][0..n) = Ac^-1 e_c for c = crow[r] (Ac is symmetric).  One warp per right-hand side; the
-// CTA's 32 warps step through the factor together so that its rows are read once per CTA (shared memory, chunks of
-// kInvChunk rows) instead of once per warp.  Each warp keeps the last hb+1 entries of its vector in shared memory.
-constexpr int kInvWarps = 32, kInvChunk = 8;
+// CTA's warps step through the factor together so that its rows are read once per CTA (shared memory, chunks of
+// kInvChunk rows, the next chunk prefetched through registers while the current one is used).  The last hb
+// entries of a warp's vector live in REGISTERS, systolically: lane l, group g holds z_{i-1-l-32g}; after a step
+// every value moves one lane up (shuffle) and the new entry enters at lane 0.
+constexpr int kInvWarps = 16, kInvChunk = 32, kInvGroups = 5;        // 5 x 32 = 160 >= hb (<= 3*46+2 = 140)
+constexpr uint32_t kInvMaxBand = 32 * kInvGroups;
 __global__ void __launch_bounds__(kInvWarps * 32)
 band_inverse_rows_kernel(const double *__restrict__ lower, const double *__restrict__ upper,
                          const double *__restrict__ invd, uint32_t n, uint32_t hb,
                          const uint32_t *__restrict__ crow, uint32_t m, double *__restrict__ out) {
     extern __shared__ double inv_smem[];
     const uint32_t W = hb + 1;
-    double *rows = inv_smem;                                       // kInvChunk * W
-    double *zwin_all = inv_smem + (size_t)kInvChunk * W;           // kInvWarps * W
+    double *rows[2] = {inv_smem, inv_smem + (size_t)kInvChunk * W};       // two chunks of factor rows
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t r = blockIdx.x * kInvWarps + warp;
     const bool live = r < m;
     const uint32_t c = live ? crow[r] : 0xffffffffu;
-    double *zwin = zwin_all + (size_t)warp * W;
     double *orow = out + (size_t)(live ? r : 0) * n;
-    for (uint32_t k = lane; k < W; k += 32) zwin[k] = 0.0;
-    const uint32_t c_first = crow[blockIdx.x * kInvWarps];         // crow ascends: nothing happens before this row
-    // ---- forward: L z = e_c ----
+    const uint32_t c_first = crow[blockIdx.x * kInvWarps];           // crow ascends: nothing happens before this row
+    const uint32_t per_thread = (kInvChunk * W + blockDim.x - 1) / blockDim.x;   // <= 32*141/512 = 9
+    double stash[9];
+    auto fetch = [&](const double *src, uint32_t row0, uint32_t nrows) {          // global -> registers
+#pragma unroll
+        for (uint32_t u = 0; u < 9; ++u) {
+            const uint32_t e = threadIdx.x + u * blockDim.x;
+            stash[u] = (u < per_thread && e < nrows * W) ? src[(size_t)row0 * W + e] : 0.0;
+        }
+    };
+    auto commit = [&](double *dst, uint32_t nrows) {                              // registers -> shared
+#pragma unroll
+        for (uint32_t u = 0; u < 9; ++u) {
+            const uint32_t e = threadIdx.x + u * blockDim.x;
+            if (u < per_thread && e < nrows * W) dst[e] = stash[u];
+        }
+    };
+    double hist[kInvGroups];                                         // hist[g] of lane l = vector entry at distance 1+l+32g
+    // ---- forward: L z = e_c, rows c_first .. n-1 ascending ----
     if (live)
         for (uint32_t i = lane; i < c_first; i += 32) orow[i] = 0.0;
-    for (uint32_t ib = c_first; ib < n; ib += kInvChunk) {
-        __syncthreads();
+#pragma unroll
+    for (int g = 0; g < kInvGroups; ++g) hist[g] = 0.0;
+    {
+        const uint32_t first_rows = min((uint32_t)kInvChunk, n - c_first);
+        fetch(lower, c_first, first_rows);
+        commit(rows[0], first_rows);
+    }
+    __syncthreads();
+    int buf = 0;
+    for (uint32_t ib = c_first; ib < n; ib += kInvChunk, buf ^= 1) {
         const uint32_t nrows = min((uint32_t)kInvChunk, n - ib);
-        for (uint32_t e = threadIdx.x; e < nrows * W; e += blockDim.x) rows[e] = lower[(size_t)ib * W + e];
-        __syncthreads();
+        const uint32_t nb = ib + kInvChunk;
+        const uint32_t next_rows = nb < n ? min((uint32_t)kInvChunk, n - nb) : 0u;
+        if (next_rows) fetch(lower, nb, next_rows);
         if (live) {
-            uint32_t pos = ib % W;                                   // slot of row i in the circular window
-            for (uint32_t q = 0; q < nrows; ++q, pos = (pos + 1 == W) ? 0u : pos + 1) {
+            double keep = 0.0;                                       // entry ib + lane, for the coalesced store
+            for (uint32_t q = 0; q < nrows; ++q) {
                 const uint32_t i = ib + q;
-                const double *Li = rows + (size_t)q * W;
+                const double *Li = rows[buf] + (size_t)q * W;
                 double s = 0.0;
-                // slots of rows before the first one hold zeros (they belong to rows still to come)
-                for (uint32_t k = 1 + lane; k <= hb; k += 32) s = fma(Li[k], zwin[pos >= k ? pos - k : pos + W - k], s);
+#pragma unroll
+                for (int g = 0; g < kInvGroups; ++g) {
+                    const uint32_t k = 1u + lane + 32u * g;
+                    if (k <= hb) s = fma(Li[k], hist[g], s);
+                }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
                 const double z = ((i == c ? 1.0 : 0.0) - s) * invd[i];
-                __syncwarp();
-                if (lane == 0) zwin[pos] = z;
-                __syncwarp();
+                if ((uint32_t)lane == q) keep = z;
+                // shift the history one lane up; the new entry enters at lane 0 of group 0
+#pragma unroll
+                for (int g = kInvGroups - 1; g >= 0; --g) {
+                    const double up = __shfl_up_sync(0xffffffffu, hist[g], 1);
+                    const double carry = g ? __shfl_sync(0xffffffffu, hist[g - 1], 31) : z;
+                    hist[g] = lane ? up : carry;
+                }
             }
-            if ((uint32_t)lane < nrows) orow[ib + lane] = zwin[(ib + lane) % W];
+            if ((uint32_t)lane < nrows) orow[ib + lane] = keep;
         }
+        if (next_rows) commit(rows[buf ^ 1], next_rows);
+        __syncthreads();
     }
-    // ---- backward: L^T x = z, in place ----
+    // ---- backward: L^T x = z, in place, rows n-1 .. 0 descending ----
+#pragma unroll
+    for (int g = 0; g < kInvGroups; ++g) hist[g] = 0.0;             // x beyond the end is zero
+    {
+        const uint32_t nrows = min((uint32_t)kInvChunk, n), ib = n - nrows;
+        fetch(upper, ib, nrows);
+        commit(rows[0], nrows);
+    }
     __syncthreads();
-    for (uint32_t k = lane; k < W; k += 32) zwin[k] = 0.0;        // x beyond the end is zero
-    for (uint32_t top = n; top > 0; top -= min((uint32_t)kInvChunk, top)) {
-        const uint32_t nrows = min((uint32_t)kInvChunk, top), ib = top - nrows;   // rows ib .. top-1, descending
-        __syncthreads();
-        for (uint32_t e = threadIdx.x; e < nrows * W; e += blockDim.x) rows[e] = upper[(size_t)ib * W + e];
-        __syncthreads();
+    buf = 0;
+    for (uint32_t top = n; top > 0; buf ^= 1) {
+        const uint32_t nrows = min((uint32_t)kInvChunk, top), ib = top - nrows;       // rows ib .. top-1
+        const uint32_t next_rows = min((uint32_t)kInvChunk, ib), nb = ib - next_rows;
+        if (next_rows) fetch(upper, nb, next_rows);
         if (live) {
-            double zreg = 0.0;
-            if ((uint32_t)lane < nrows) zreg = orow[ib + lane];
-            uint32_t pos = (top - 1) % W;
-            for (uint32_t qq = nrows; qq > 0; --qq, pos = (pos == 0) ? W - 1 : pos - 1) {
+            const double zreg = (uint32_t)lane < nrows ? orow[ib + lane] : 0.0;
+            double keep = 0.0;
+            for (uint32_t qq = nrows; qq > 0; --qq) {
                 const uint32_t q = qq - 1, i = ib + q;
-                const double *Ui = rows + (size_t)q * W;
+                const double *Ui = rows[buf] + (size_t)q * W;
                 double s = 0.0;
-                for (uint32_t k = 1 + lane; k <= hb; k += 32) s = fma(Ui[k], zwin[pos + k >= W ? pos + k - W : pos + k], s);
+#pragma unroll
+                for (int g = 0; g < kInvGroups; ++g) {
+                    const uint32_t k = 1u + lane + 32u * g;
+                    if (k <= hb) s = fma(Ui[k], hist[g], s);
+                }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-                const double zi = __shfl_sync(0xffffffffu, zreg, (int)q);
-                const double x = (zi - s) * invd[i];
-                __syncwarp();
-                if (lane == 0) zwin[pos] = x;
-                __syncwarp();
+                const double x = (__shfl_sync(0xffffffffu, zreg, (int)q) - s) * invd[i];
+                if ((uint32_t)lane == q) keep = x;
+#pragma unroll
+                for (int g = kInvGroups - 1; g >= 0; --g) {
+                    const double up = __shfl_up_sync(0xffffffffu, hist[g], 1);
+                    const double carry = g ? __shfl_sync(0xffffffffu, hist[g - 1], 31) : x;
+                    hist[g] = lane ? up : carry;
+                }
             }
-            if ((uint32_t)lane < nrows) orow[ib + lane] = zwin[(ib + lane) % W];
+            if ((uint32_t)lane < nrows) orow[ib + lane] = keep;
         }
+        if (next_rows) commit(rows[buf ^ 1], next_rows);
+        __syncthreads();
+        top = ib;
     }
 }
 
@@ -386,17 +482,22 @@ coarse_restrict_kernel(const uint32_t *__restrict__ lagg, const uint32_t *__rest
     const uint32_t I = lagg[blockIdx.x];
     double a[3] = {0.0, 0.0, 0.0};
     const uint32_t s1 = agg_ptr[I + 1];
-    for (uint32_t s = agg_ptr[I] + threadIdx.x; s < s1; s += 2 * kRestrictThreads) {
-        const uint32_t s2 = s + kRestrictThreads;                 // two independent gathers in flight
-        const bool two = s2 < s1;
-        const uint32_t pa0 = perm_ax[s], pa1 = two ? perm_ax[s2] : 0u;
-        const double t0 = rot_perm[s], t1 = two ? rot_perm[s2] : 0.0;
-        const double r0 = r[row_lo + (pa0 >> 2)], r1 = two ? r[row_lo + (pa1 >> 2)] : 0.0;
-        a[pa0 & 3u] += r0;
-        a[2] = fma(t0, r0, a[2]);
-        if (two) {
-            a[pa1 & 3u] += r1;
-            a[2] = fma(t1, r1, a[2]);
+    for (uint32_t s = agg_ptr[I] + threadIdx.x; s < s1; s += 4 * kRestrictThreads) {
+        uint32_t pa[4];                                           // four independent gathers in flight
+        double tq[4], rq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t su = s + u * kRestrictThreads;
+            pa[u] = su < s1 ? perm_ax[su] : 0xffffffffu;
+            tq[u] = su < s1 ? rot_perm[su] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) rq[u] = pa[u] != 0xffffffffu ? r[row_lo + (pa[u] >> 2)] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                             // fixed order: the same sums in every run
+            if (pa[u] == 0xffffffffu) continue;
+            if (pa[u] & 1u) a[1] += rq[u]; else a[0] += rq[u];
+            a[2] = fma(tq[u], rq[u], a[2]);
         }
     }
     __shared__ double red[3][kRestrictThreads / 32];
@@ -426,51 +527,64 @@ coarse_restrict_kernel(const uint32_t *__restrict__ lagg, const uint32_t *__rest
     }
 }
 
-// y = (rows of Ac^-1) w and this rank's share of w.y.  Every CTA first builds the complete w in shared memory
-// (the partials of the ranks that touch an aggregate, added in rank order: the same bits on every rank), then
-// its warps take rows.  The share of w.y goes to *wy_out, or into the mailboxes when links.n > 0.
+// w = sum over the ranks of their partial restrictions, added in rank order (the same bits on every rank).
 __global__ void __launch_bounds__(256)
-coarse_apply_kernel(const double *__restrict__ Ainv, const uint32_t *__restrict__ crow,
-                    const uint8_t *__restrict__ wy_mine, const uint16_t *__restrict__ touch, uint32_t m, uint32_t nc,
-                    int step, CoarseLinks clinks, PeerLinks links, double *__restrict__ y,
-                    double *__restrict__ partials, unsigned *__restrict__ ticket, PcgScalars *sc,
-                    double *__restrict__ wy_out) {
+coarse_gather_w_kernel(const uint16_t *__restrict__ touch, uint32_t nc, int step, CoarseLinks clinks,
+                       double *__restrict__ w, PcgScalars *sc) {
     if (sc->stop) return;
-    extern __shared__ double w_s[];
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nc) return;
     const uint32_t seq = ll_seq(sc, step < 0 ? 0ull : sc->chunk_base + (unsigned long long)step + 1ull);
     const int parity = step < 0 ? 0 : (step & 1);
     const LLWord *mine = clinks.wbuf[clinks.me] + (size_t)parity * kMaxRanks * kCoarseMax;
-    for (uint32_t j = threadIdx.x; j < nc; j += blockDim.x) {
-        uint32_t tm = touch[j / 3u];
-        double s = 0.0;
-        while (tm) {
-            const int src = __ffs(tm) - 1;
-            tm &= tm - 1u;
-            s += ll_wait(mine + (size_t)src * kCoarseMax + j, seq, sc);
-        }
-        w_s[j] = s;
+    uint32_t tm = touch[j / 3u];
+    double s = 0.0;
+    while (tm) {
+        const int src = __ffs(tm) - 1;
+        tm &= tm - 1u;
+        s += ll_wait(mine + (size_t)src * kCoarseMax + j, seq, sc);
     }
-    __syncthreads();
+    w[j] = s;
+}
+
+// y = (this rank's rows of Ac^-1) w, one warp per row, and this rank's share of w.y — to *wy_out, or into the
+// mailboxes when links.n > 0.
+__global__ void __launch_bounds__(256)
+coarse_apply_kernel(const double *__restrict__ Ainv, const uint32_t *__restrict__ crow,
+                    const uint8_t *__restrict__ wy_mine, const double *__restrict__ w, uint32_t m, uint32_t nc,
+                    int step, PeerLinks links, double *__restrict__ y, double *__restrict__ partials,
+                    unsigned *__restrict__ ticket, PcgScalars *sc, double *__restrict__ wy_out) {
+    if (sc->stop) return;
     const int lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     double dot = 0.0;
     for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < m; i += warps) {
         const double *a = Ainv + (size_t)i * nc;
-        double acc = 0.0;
-        for (uint32_t c = lane; c < nc; c += 32) acc = fma(__ldcs(a + c), w_s[c], acc);
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+        uint32_t c = lane;
+        for (; c + 96 < nc; c += 128) {
+            const double a0 = __ldcs(a + c), a1 = __ldcs(a + c + 32), a2 = __ldcs(a + c + 64), a3 = __ldcs(a + c + 96);
+            acc0 = fma(a0, __ldg(w + c), acc0);
+            acc1 = fma(a1, __ldg(w + c + 32), acc1);
+            acc2 = fma(a2, __ldg(w + c + 64), acc2);
+            acc3 = fma(a3, __ldg(w + c + 96), acc3);
+        }
+        for (; c < nc; c += 32) acc0 = fma(__ldcs(a + c), __ldg(w + c), acc0);
+        double acc = (acc0 + acc1) + (acc2 + acc3);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
         if (lane == 0) {
             const uint32_t row = crow[i];
             y[row] = acc;
-            if (wy_mine[i]) dot = fma(w_s[row], acc, dot);
+            if (wy_mine[i]) dot = fma(__ldg(w + row), acc, dot);
         }
     }
     double v[1] = {dot};
     double tot[1] = {0.0};
     const bool last = grid_sum_256<1>(v, partials, ticket, tot);
     if (links.n) {
-        if (grid_is_last_cta()) mailbox_post(links, kMailWy, parity, tot[0], 0.0, seq);
+        const uint32_t seq = ll_seq(sc, step < 0 ? 0ull : sc->chunk_base + (unsigned long long)step + 1ull);
+        if (grid_is_last_cta()) mailbox_post(links, kMailWy, step < 0 ? 0 : (step & 1), tot[0], 0.0, seq);
     } else if (last) {
         *wy_out = tot[0];
     }

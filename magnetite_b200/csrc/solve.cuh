@@ -230,11 +230,12 @@ static void enqueue_coarse_solve(mag_ctx *ctx, std::vector<RankState> &ranks, co
     const bool local_sum = m.reduce == Reduce::kNccl || m.reduce == Reduce::kEmulated;
     for (RankState &W : ranks) {
         CoarseSpace &C = W.S->coarse;
-        const unsigned grid = std::max(1u, std::min(cdiv((size_t)C.m * 32, 256), (unsigned)ctx->sm_count * 2u));
-        MAG_LAUNCH(ctx, coarse_apply_kernel, grid, 256, (size_t)C.nc * sizeof(double), (const double *)C.Ainv.p,
-                   (const uint32_t *)C.crow.p, (const uint8_t *)C.wy_mine.p, (const uint16_t *)C.touch.p, C.m, C.nc, step,
-                   C.links, links_of(W, m), C.y.p, C.partials.p, C.ticket.p, W.scal.p,
-                   scal_field(W, local_sum ? kOffLocWy : kOffWy));
+        MAG_LAUNCH(ctx, coarse_gather_w_kernel, cdiv(C.nc, 256), 256, 0, (const uint16_t *)C.touch.p, C.nc, step, C.links,
+                   C.w.p, W.scal.p);
+        const unsigned grid = std::max(1u, std::min(cdiv((size_t)C.m * 32, 256), (unsigned)ctx->sm_count * 8u));
+        MAG_LAUNCH(ctx, coarse_apply_kernel, grid, 256, 0, (const double *)C.Ainv.p, (const uint32_t *)C.crow.p,
+                   (const uint8_t *)C.wy_mine.p, (const double *)C.w.p, C.m, C.nc, step, links_of(W, m), C.y.p,
+                   C.partials.p, C.ticket.p, W.scal.p, scal_field(W, local_sum ? kOffLocWy : kOffWy));
     }
     reduce_scalars(ctx, ranks, m, kOffLocWy, kOffWy, 1);
 }
@@ -387,7 +388,7 @@ static bool setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
         C.Ac_compact.alloc(ctx, (size_t)C.n_agg * 81);
         DevBuf<int> far(ctx, 1);
         far.zero();
-        MAG_LAUNCH(ctx, coarse_galerkin_kernel, C.n_agg, 96, 0, (const uint32_t *)C.agg_ptr.p, (const uint32_t *)C.perm_ax.p,
+        MAG_LAUNCH(ctx, coarse_galerkin_kernel, C.n_agg, kGalerkinWarps * 32, 0, (const uint32_t *)C.agg_ptr.p, (const uint32_t *)C.perm_ax.p,
                    (const uint32_t *)S->Kff.rowptr.p, (const int32_t *)S->Kff.col.p, (const double *)S->Kff.val.p,
                    (const uint32_t *)C.mode.p, (const double *)C.rot.p, S->row_lo, g, C.Ac_compact.p, far.p);
         int h_far = 0;
@@ -395,8 +396,8 @@ static bool setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
         MAG_CUDA(cudaStreamSynchronize(ctx->stream));
         if (h_far) fail(MAG_ERR_BAD_ARG, "two-level preconditioner: an element spans non-adjacent aggregates "
                                           "(%u x %u boxes are too small for this mesh); lower coarse_aggregates", g.nbx, g.nby);
-        C.y.alloc(ctx, C.nc);
-        C.y.zero();
+        C.y.alloc(ctx, C.nc); C.w.alloc(ctx, C.nc);
+        C.y.zero(); C.w.zero();
         C.partials.alloc(ctx, 2 * (size_t)ctx->sm_count * 8);
         C.ticket.alloc(ctx, 1);
         C.ticket.zero();
@@ -454,12 +455,12 @@ static bool setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
         MAG_LAUNCH(ctx, band_transpose_kernel, cdiv((size_t)nc * Wb, 256), 256, 0, (const double *)lower.p, nc, hb, upper.p);
         C.Ainv.alloc(ctx, (size_t)std::max(C.m, 1u) * nc);
         if (C.m) {
-            const size_t inv_smem = ((size_t)kInvChunk + kInvWarps) * Wb * sizeof(double);
+            if (hb > kInvMaxBand) fail(MAG_ERR_BAD_ARG, "two-level preconditioner: band of %u exceeds the substitution kernel's %u", hb, kInvMaxBand);
+            const size_t inv_smem = 2 * (size_t)kInvChunk * Wb * sizeof(double);
             MAG_CUDA(cudaFuncSetAttribute(band_inverse_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem));
             MAG_LAUNCH(ctx, band_inverse_rows_kernel, cdiv(C.m, kInvWarps), kInvWarps * 32, inv_smem, (const double *)lower.p,
                        (const double *)upper.p, (const double *)invd.p, nc, hb, (const uint32_t *)C.crow.p, C.m, C.Ainv.p);
         }
-        MAG_CUDA(cudaFuncSetAttribute(coarse_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCoarseMax * sizeof(double))));
         // single rank without a shared slab: its own buffer for the partial restrictions
         if (!S->shared_slab) {
             C.wbuf_local.alloc(ctx, kCoarseWbufWords);
