@@ -142,7 +142,7 @@ int mag_abi_version(void);
 const char *mag_last_error(void);
 int mag_device_count(int *count);
 int mag_ctx_create(mag_ctx **ctx, int device);
-void mag_ctx_destroy(mag_ctx *ctx);
+void mag_ctx_destroy(mag_ctx *ctx);       /* collective on a context that has a communicator (mag_comm_init) */
 void mag_options_default(mag_options *opt);
 
 /* ---- the drop-in call: replaces solver::run (src/solver.rs:543-586) ------ */
@@ -157,7 +157,7 @@ int mag_assemble(mag_ctx *ctx, const mag_mesh *mesh, const mag_material *mat,
 /* CG on the assembled system + scatter + reactions + stress; replaces
  * solver.rs:435-482 and :578-583. */
 int mag_system_solve(mag_system *sys, const mag_options *opt, mag_result *out, mag_stats *stats);
-void mag_system_free(mag_system *sys);   /* multi-GPU: collective (ranks meet before exported buffers are freed) */
+void mag_system_free(mag_system *sys);
 int mag_system_info(const mag_system *sys, mag_stats *stats);
 
 /* parity exports (host buffers, caller-allocated from mag_system_info sizes) */

@@ -103,8 +103,23 @@ extern "C" void mag_ctx_destroy(mag_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->own_stream);
     if (ctx->comm) {
-        if (ctx->comm->nccl) ncclCommDestroy(ctx->comm->nccl);
-        delete ctx->comm;
+        Comm *c = ctx->comm;
+        // every rank unmaps its peers' slabs, then all ranks meet, and only then does anyone free the buffer it
+        // exported (freeing memory another process still maps is undefined)
+        for (int r = 0; r < (int)c->peer_slab.size(); ++r)
+            if (r != c->rank && c->peer_slab[r]) cudaIpcCloseMemHandle(c->peer_slab[r]);
+        if (c->slab && c->nccl) {
+            int *token = nullptr;
+            if (cudaMalloc((void **)&token, sizeof(int)) == cudaSuccess) {
+                cudaMemset(token, 0, sizeof(int));
+                if (ncclAllReduce(token, token, 1, ncclInt, ncclSum, c->nccl, ctx->own_stream) == ncclSuccess)
+                    cudaStreamSynchronize(ctx->own_stream);
+                cudaFree(token);
+            }
+        }
+        if (c->slab) cudaFree(c->slab);
+        if (c->nccl) ncclCommDestroy(c->nccl);
+        delete c;
     }
     ctx->heap.destroy();
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -157,19 +172,7 @@ extern "C" void mag_system_free(mag_system *sys) {
         cudaSetDevice(ctx->device);
         ctx->stream = ctx->own_stream;
     }
-    // Multi-GPU: collective.  Every rank unmaps its peers' halo buffers, then all ranks meet, and only
-    // then does anyone free the buffer it exported (freeing memory another process still maps is undefined).
-    if (ctx && ctx->comm && sys->nranks > 1 && sys->shared_slab) {
-        for (void *p : sys->ipc_opened) cudaIpcCloseMemHandle(p);
-        sys->ipc_opened.clear();
-        try {
-            DevBuf<int> token(ctx, 1);
-            token.zero();
-            if (ncclAllReduce(token.p, token.p, 1, ncclInt, ncclSum, ctx->comm->nccl, ctx->stream) == ncclSuccess)
-                cudaStreamSynchronize(ctx->stream);
-        } catch (...) {
-        }
-    }
+    // (the halo slab and its IPC mappings belong to the communicator: nothing collective happens here)
     delete sys;
     if (ctx) cudaStreamSynchronize(ctx->own_stream);
 }

@@ -19,6 +19,16 @@ namespace mag {
 struct Comm {
     ncclComm_t nccl = nullptr;
     int rank = 0, nranks = 1;
+    // The slab the other ranks store into (Dinv halo, mailboxes, coarse partials, halo of r: solve.cuh) and its CUDA
+    // IPC mappings belong to the communicator, not to a system: allocating, exporting and mapping 100+ MB costs tens
+    // of milliseconds, a solve a few.  It grows when a system needs more; `generation` tells a system that holds
+    // pointers into an older slab to look them up again.  `epoch` numbers the solves: the sequence numbers of all
+    // messages derive from it, so nothing in the slab ever has to be reset between solves or systems.
+    double *slab = nullptr;
+    size_t slab_bytes = 0;
+    std::vector<double *> peer_slab;        // rank r's slab as mapped here (own rank: slab)
+    unsigned long long generation = 0, epoch = 0;
+    size_t layout_rows = 0;                 // ext_len of the system layout the slab was last used with
 };
 
 // Blocking allgather of `count` uint32 per rank (host in, host out).

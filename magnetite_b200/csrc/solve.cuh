@@ -43,11 +43,52 @@ inline LLWord *slab_halo(const mag_system *S, double *slab) { return slab_wbuf(S
 
 // Plain cudaMalloc so it can be exported through CUDA IPC.  Mailbox and halo buffer start
 // zeroed and are never reset afterwards (sequence numbers only move forward).
-static void ensure_shared_slab(mag_system *S) {
+static void ensure_shared_slab(mag_system *S) {      // virtual ranks (one process): every system owns its slab
     if (S->shared_slab) return;
     MAG_CUDA(cudaMalloc((void **)&S->shared_slab, slab_bytes(S)));
     MAG_CUDA(cudaMemset(S->shared_slab, 0, slab_bytes(S)));
     MAG_CUDA(cudaDeviceSynchronize());
+    S->owns_slab = true;
+}
+
+// All ranks meet on the stream (a one-word NCCL allreduce).
+static void comm_barrier(mag_ctx *ctx) {
+    DevBuf<int> token(ctx, 1);
+    token.zero();
+    MAG_NCCL(ncclAllReduce(token.p, token.p, 1, ncclInt, ncclSum, ctx->comm->nccl, ctx->stream));
+    MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// Collective: the communicator's slab holds at least `bytes` afterwards (the same `bytes` on every rank).
+static void comm_ensure_slab(mag_ctx *ctx, size_t bytes) {
+    Comm *c = ctx->comm;
+    if (c->slab && c->slab_bytes >= bytes) return;
+    const int R = c->nranks;
+    if (R > kMaxRanks) fail(MAG_ERR_BAD_ARG, "at most %d ranks", kMaxRanks);
+    if (c->slab) {                          // nobody may free a buffer a peer still has mapped
+        for (int r = 0; r < R; ++r)
+            if (r != c->rank && c->peer_slab[r]) cudaIpcCloseMemHandle(c->peer_slab[r]);
+        comm_barrier(ctx);
+        cudaFree(c->slab);
+        c->slab = nullptr; c->slab_bytes = 0;
+    }
+    const size_t want = ((bytes + bytes / 4) + ((size_t)64 << 20) - 1) & ~(((size_t)64 << 20) - 1);   // headroom, 64 MiB steps
+    MAG_CUDA(cudaMalloc((void **)&c->slab, want));
+    MAG_CUDA(cudaMemset(c->slab, 0, want));
+    MAG_CUDA(cudaDeviceSynchronize());
+    c->slab_bytes = want;
+    cudaIpcMemHandle_t h;
+    MAG_CUDA(cudaIpcGetMemHandle(&h, c->slab));
+    std::vector<cudaIpcMemHandle_t> hs(R);
+    allgather_bytes(ctx, &h, sizeof h, hs.data());
+    c->peer_slab.assign(R, nullptr);
+    for (int r = 0; r < R; ++r) {
+        if (r == c->rank) { c->peer_slab[r] = c->slab; continue; }
+        void *p = nullptr;      // every rank is mapped: the mailbox allreduce posts to all of them
+        MAG_CUDA(cudaIpcOpenMemHandle(&p, hs[r], cudaIpcMemLazyEnablePeerAccess));
+        c->peer_slab[r] = static_cast<double *>(p);
+    }
+    ++c->generation;
 }
 
 // Which of MY rows do the other ranks need?  Pure host logic (also exported as
@@ -95,31 +136,36 @@ static void build_push_segments(mag_system *S, const std::vector<uint32_t> &ext_
     S->push_ready = true;
 }
 
-// Production: exchange halo extents and IPC handles with the other processes.
+// Production: exchange the halo extents with the other processes and point this system at the communicator's slab.
 static void setup_halo_ipc(mag_ctx *ctx, mag_system *S) {
-    if (S->push_ready) return;
+    Comm *c = ctx->comm;
+    if (S->push_ready && S->slab_generation == c->generation) return;
     const int R = S->nranks;
-    ensure_shared_slab(S);
     std::vector<uint32_t> mine = {S->ext_lo, S->ext_hi}, all(2 * (size_t)R);
     allgather_u32(ctx, mine.data(), 2, all.data());
     std::vector<uint32_t> elo(R), ehi(R);
-    for (int r = 0; r < R; ++r) { elo[r] = all[2 * r]; ehi[r] = all[2 * r + 1]; }
-    cudaIpcMemHandle_t h;
-    MAG_CUDA(cudaIpcGetMemHandle(&h, S->shared_slab));
-    std::vector<cudaIpcMemHandle_t> hs(R);
-    allgather_bytes(ctx, &h, sizeof h, hs.data());
-    if (R > kMaxRanks) fail(MAG_ERR_BAD_ARG, "at most %d ranks", kMaxRanks);
-    std::vector<double *> peer(R, nullptr);
+    size_t halo_max = 0;
     for (int r = 0; r < R; ++r) {
-        if (r == S->rank) { peer[r] = S->shared_slab; continue; }
-        void *p = nullptr;      // every rank is mapped: the mailbox allreduce posts to all of them
-        MAG_CUDA(cudaIpcOpenMemHandle(&p, hs[r], cudaIpcMemLazyEnablePeerAccess));
-        S->ipc_opened.push_back(p);
-        peer[r] = static_cast<double *>(p);
+        elo[r] = all[2 * r]; ehi[r] = all[2 * r + 1];
+        halo_max = std::max(halo_max, (size_t)(S->all_row_lo[r] - elo[r]) + (size_t)(ehi[r] - S->all_row_lo[r + 1]));
     }
+    // the same number on every rank: the layout depends on n_free only, the halo part is sized for the widest rank
+    const size_t need = slab_bytes(S) - (halo_count(S) + 1) * sizeof(LLWord) + (halo_max + 1) * sizeof(LLWord);
+    comm_ensure_slab(ctx, need);
+    if (c->layout_rows != ext_len(S)) {
+        // another layout than the last system's: what were plain doubles (Dinv) may now lie where self-validating
+        // words are read.  Start from zeros (never a valid sequence number); all ranks, before anyone writes.
+        comm_barrier(ctx);
+        MAG_CUDA(cudaMemsetAsync(c->slab, 0, c->slab_bytes, ctx->stream));
+        comm_barrier(ctx);
+        c->layout_rows = ext_len(S);
+    }
+    S->shared_slab = c->slab;
+    S->owns_slab = false;
+    S->slab_generation = c->generation;
     S->links.n = R; S->links.me = S->rank;
-    for (int r = 0; r < R; ++r) S->links.box[r] = slab_mailbox(S, peer[r]);
-    build_push_segments(S, elo, ehi, peer);
+    for (int r = 0; r < R; ++r) S->links.box[r] = slab_mailbox(S, c->peer_slab[r]);
+    build_push_segments(S, elo, ehi, c->peer_slab);
 }
 
 static void rank_alloc(mag_ctx *ctx, RankState &W, mag_system *S) {
@@ -232,10 +278,19 @@ static void enqueue_coarse_solve(mag_ctx *ctx, std::vector<RankState> &ranks, co
         CoarseSpace &C = W.S->coarse;
         MAG_LAUNCH(ctx, coarse_gather_w_kernel, cdiv(C.nc, 256), 256, 0, (const uint16_t *)C.touch.p, C.nc, step, C.links,
                    C.w.p, W.scal.p);
-        const unsigned grid = std::max(1u, std::min(cdiv((size_t)C.m * 32, 256), (unsigned)ctx->sm_count * 8u));
-        MAG_LAUNCH(ctx, coarse_apply_kernel, grid, 256, 0, (const double *)C.Ainv.p, (const uint32_t *)C.crow.p,
-                   (const uint8_t *)C.wy_mine.p, (const double *)C.w.p, C.m, C.nc, step, links_of(W, m), C.y.p,
-                   C.partials.p, C.ticket.p, W.scal.p, scal_field(W, local_sum ? kOffLocWy : kOffWy));
+        // enough rows to fill the machine with one warp each (a single GPU): warp per row; else a CTA per row
+        const unsigned warp_ctas = cdiv((size_t)C.m * 32, 256);
+        if (warp_ctas >= (unsigned)ctx->sm_count * 4u) {
+            MAG_LAUNCH(ctx, coarse_apply_warp_kernel, std::min(warp_ctas, (unsigned)ctx->sm_count * 8u), 256, 0,
+                       (const double *)C.Ainv.p, (const uint32_t *)C.crow.p, (const uint8_t *)C.wy_mine.p,
+                       (const double *)C.w.p, C.m, C.nc, step, links_of(W, m), C.y.p, C.partials.p, C.ticket.p,
+                       W.scal.p, scal_field(W, local_sum ? kOffLocWy : kOffWy));
+        } else {
+            const unsigned grid = std::max(1u, std::min(C.m, (unsigned)ctx->sm_count * 8u));
+            MAG_LAUNCH(ctx, coarse_apply_kernel, grid, 256, 0, (const double *)C.Ainv.p, (const uint32_t *)C.crow.p,
+                       (const uint8_t *)C.wy_mine.p, (const double *)C.w.p, C.m, C.nc, step, links_of(W, m), C.y.p,
+                       C.partials.p, C.ticket.p, W.scal.p, scal_field(W, local_sum ? kOffLocWy : kOffWy));
+        }
     }
     reduce_scalars(ctx, ranks, m, kOffLocWy, kOffWy, 1);
 }
@@ -518,7 +573,20 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
     for (RankState &W : ranks) {
         PcgScalars z;
         std::memset(&z, 0, sizeof z);
-        z.epoch = ++W.S->solve_epoch;      // the same on every rank: solves are collective
+        // the same on every rank: solves are collective.  Production: the communicator counts (its slab outlives systems)
+        Comm *cm = (ranks.size() == 1 && W.S->nranks > 1) ? ctx->comm : nullptr;
+        if (cm) {
+            if (++cm->epoch % 255ull == 0) {            // the 8-bit epoch tag wraps: forget every old message first
+                comm_barrier(ctx);
+                const size_t off = ext_len(W.S) * sizeof(double);
+                MAG_CUDA(cudaMemsetAsync(reinterpret_cast<char *>(cm->slab) + off, 0, cm->slab_bytes - off, ctx->stream));
+                comm_barrier(ctx);
+            }
+            W.S->solve_epoch = cm->epoch;
+        } else {
+            ++W.S->solve_epoch;
+        }
+        z.epoch = W.S->solve_epoch;
         z.tune = ctx->tune;
         MAG_CUDA(cudaMemcpyAsync(W.scal.p, &z, sizeof z, cudaMemcpyHostToDevice, ctx->stream));
     }

@@ -42,8 +42,9 @@ struct mag_system {
     mag::DevBuf<double> rhs, diag;           // owned rows
     mag::SellMatrix sell;
     // halo buffers other ranks store into (plain cudaMalloc: exported through CUDA IPC)
-    double *shared_slab = nullptr;           // [ Dinv (global-indexed) | mailbox | halo buffer of r ]
-    std::vector<void *> ipc_opened;
+    double *shared_slab = nullptr;           // [ Dinv (global-indexed) | mailbox | coarse partials | halo buffer of r ]
+    bool owns_slab = false;                  // virtual ranks own theirs; production systems borrow the communicator's
+    unsigned long long slab_generation = 0;  // Comm::generation the pointers below were taken from
     mag::CoarseSpace coarse;                 // two-level preconditioner (built on first use)
     mag::PushSegs push;
     mag::PeerLinks links;                    // peer mailboxes (production multi-rank only)
@@ -54,8 +55,7 @@ struct mag_system {
     mag_stats stats{};
 
     ~mag_system() {
-        for (void *p : ipc_opened) cudaIpcCloseMemHandle(p);
-        if (shared_slab) cudaFree(shared_slab);
+        if (shared_slab && owns_slab) cudaFree(shared_slab);
     }
 };
 
