@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cmath>
 
+#include "small.cuh"
 #include "system.cuh"
 
 namespace mag {
@@ -543,6 +544,58 @@ struct SolveOutcome {
     bool rerun_best = false;
 };
 
+// Systems that fit one thread-block cluster's shared memory (small.cuh): the whole solve in one kernel.
+// Returns false when the system does not fit (or the cluster cannot be launched): the caller takes the general path.
+static bool small_cg_try(mag_ctx *ctx, RankState &W, const mag_options &opt, int jacobi, bool compat, SolveOutcome &out) {
+    mag_system *S = W.S;
+    const CsrMatrix &A = S->Kff;
+    const uint32_t n = A.n_rows;
+    if ((ctx->tune & 128) || n == 0 || n > 65535u || A.nnz > (1u << 22)) return false;
+    std::vector<uint32_t> h_rowptr((size_t)n + 1);
+    MAG_CUDA(cudaMemcpyAsync(h_rowptr.data(), A.rowptr.p, h_rowptr.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+    SmallArgs a{};
+    unsigned C = 0;
+    size_t smem = 0;
+    for (unsigned c : {8u, 16u}) {
+        const size_t need = small_cg_smem(n, A.nnz, c, &a.rows_per_cta, &a.nnz_cap, &a.n_pad, h_rowptr);
+        if (need && need <= 200 * 1024) { C = c; smem = need; break; }
+    }
+    if (!C) return false;
+    a.rowptr = A.rowptr.p; a.col = A.col.p; a.val = A.val.p; a.b = S->rhs.p; a.diag = S->diag.p; a.x = W.x.p;
+    a.n = n; a.jacobi = jacobi; a.compat = compat ? 1 : 0;
+    a.rel_tol2 = opt.rel_tol * opt.rel_tol;
+    a.abs_thr2 = opt.cost_kind == 1 ? opt.abs_tol : opt.abs_tol * opt.abs_tol;
+    a.max_iter = opt.max_iter;
+    a.out = W.scal.p;
+    if (cudaFuncSetAttribute(small_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        (C > 8 && cudaFuncSetAttribute(small_cg_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) {
+        cudaGetLastError();
+        return false;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(C); cfg.blockDim = dim3(kSmallThreads); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, small_cg_kernel, &cfg) != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError();
+        return false;
+    }
+    if (cudaLaunchKernelEx(&cfg, small_cg_kernel, a) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    ctx->launches++;
+    MAG_CUDA(cudaMemcpyAsync(&out.hs, W.scal.p, sizeof out.hs, cudaMemcpyDeviceToHost, ctx->stream));
+    MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+    out.bb = out.hs.rzc[0];
+    out.precond_used = compat ? 0 : (jacobi ? 1 : 0);
+    return true;
+}
+
 // Runs CG over `ranks` (size 1 in production).  All ranks see identical scalars.
 static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const mag_options &opt) {
     SolveMode mode;
@@ -561,6 +614,10 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
     PcgScalars &hs = out.hs;
     const uint32_t n_glob = ranks[0].S->n_free;
     if (n_glob == 0) { hs.stop = 1; return out; }
+    // one rank, no coarse space, small enough for one cluster's shared memory: the single-kernel solve
+    if (ranks.size() == 1 && ranks[0].S->nranks == 1 && !mode.two_level && mode.format != 1 &&
+        small_cg_try(ctx, ranks[0], opt, jacobi, compat, out))
+        return out;
     if (mode.two_level) {
         EventTimer t(ctx->stream);
         t.start();

@@ -467,6 +467,43 @@ def test_two_level_on_examples_and_indefinite_meshes(ctx):
     assert small.stats["precond_used"] == 1 and large.stats["precond_used"] == 2
 
 
+def test_single_cluster_solve_matches_the_general_path(ctx):
+    """Systems that fit one thread-block cluster's shared memory are solved by ONE kernel (small.cuh); MAG_TUNE=128
+    switches it off.  Both paths run the same recurrence: same iteration counts (to rounding), same answers, for
+    the reference's semantics (compat, with and without a max_iters end), Jacobi-PCG, and a negative-definite mesh."""
+    import os
+    os.environ["MAG_TUNE"] = "128"
+    try:
+        general = _lib.Context(0)
+    finally:
+        del os.environ["MAG_TUNE"]
+    try:
+        g = np.load(GOLDEN / "example_linkedin.npz")
+        t = np.load(GOLDEN / "example_tensile.npz")
+        cases = [(golden_mesh(g), META.__class__(*g["material"])), (golden_mesh(t), META.__class__(*t["material"])),
+                 (meshgen.jitter(meshgen.plate(40, 20)), META), (meshgen.plate(3, 2), META)]
+        for mesh, meta in cases:
+            for opt in (dict(compat=1), dict(precond=1, rel_tol=1e-12), dict(compat=1, max_iter=37), dict(precond=0)):
+                a = solver.solve_soa(mesh, meta, ctx, _lib.default_options(**opt)) if "max_iter" not in opt else None
+                if a is None:                      # max_iter ends the run: both paths return argmin's best_param
+                    with solver.System(mesh, meta, ctx) as S:
+                        a = S.solve(_lib.default_options(**opt), allow_not_converged=True)
+                    with solver.System(mesh, meta, general) as S:
+                        b = S.solve(_lib.default_options(**opt), allow_not_converged=True)
+                else:
+                    b = solver.solve_soa(mesh, meta, general, _lib.default_options(**opt))
+                assert a.stats["kernel_launches"] < b.stats["kernel_launches"]            # one CG kernel against a graph of them
+                assert abs(int(a.stats["iters"]) - int(b.stats["iters"])) <= max(2, int(b.stats["iters"]) // 50), opt
+                assert a.stats["converged"] == b.stats["converged"] and a.stats["negative_definite"] == b.stats["negative_definite"]
+                ua, ub = np.concatenate([a.ux, a.uy]), np.concatenate([b.ux, b.uy])
+                tol = 1e-9 if a.stats["converged"] else 1e-6
+                assert rel_l2(ua, ub) < tol, (opt, rel_l2(ua, ub))
+        again = [solver.solve_soa(cases[0][0], cases[0][1], ctx, _lib.default_options(compat=1)) for _ in range(2)]
+        assert again[0].ux.tobytes() == again[1].ux.tobytes()                               # bit-identical run to run
+    finally:
+        general.close()
+
+
 def test_narrow_and_wide_sell_index_streams_agree(ctx):
     """16-bit column offsets (banded numbering) and 32-bit absolute columns carry the same matrix:
     identical SpMV results and identical CG iterates; unstructured numbering falls back to 32 bits."""
