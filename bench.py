@@ -648,12 +648,17 @@ def run_ours(args):
         out_h["stress"] = torch.empty(E, dtype=torch.float64).pin_memory()
         res_h = _lib.MagResult(out_h["ux"].data_ptr(), out_h["uy"].data_ptr(), out_h["fx"].data_ptr(),
                                out_h["fy"].data_ptr(), out_h["stress"].data_ptr(), None, 0)
-        h2d = N * (8 * 6 + 1) + E * 12
+        h2d = N * (8 * 6 + 1) + E * 12                   # whole job (at N > 1 every rank moves 1/N of it)
         d2h = N * 32 + E * 8
+
+        # N > 1: every rank passes the whole host mesh (the library moves each array over PCIe once per job: every rank
+        # uploads its 1/N slice, the slices travel over NVLink) and reads back its 1/N slice of the result arrays
+        # (mag_options.result_scope = 1): the job's inputs and results cross PCIe once, like at N = 1.
+        opt_e = options(result_scope=1) if world > 1 else opt
 
         def host_step():
             s = _lib.MagStats()
-            _lib.check(lib.mag_solve(ctx.handle, C.byref(hm), C.byref(mat), C.byref(opt), C.byref(res_h), C.byref(s)),
+            _lib.check(lib.mag_solve(ctx.handle, C.byref(hm), C.byref(mat), C.byref(opt_e), C.byref(res_h), C.byref(s)),
                        "mag_solve(host)")
             return s
 
@@ -668,10 +673,22 @@ def run_ours(args):
         barrier()
         ms_e2e = max_over_ranks(ev0.elapsed_time(ev1)) / e_steps
         # what came back over PCIe is what the device-resident step computed
-        same = bool(torch.equal(out_h["ux"], out_d["ux"].cpu()) and torch.equal(out_h["stress"], out_d["stress"].cpu()))
+        if world > 1:                                    # this rank's slice of the result, bit for bit
+            nlo, nhi = mdist.partition_nodes(N, world, rank)
+            elo, ehi = mdist.partition_nodes(E, world, rank)
+            ok = bool(torch.equal(out_h["ux"][nlo:nhi], out_d["ux"][nlo:nhi].cpu()) and
+                      torch.equal(out_h["fy"][nlo:nhi], out_d["fy"][nlo:nhi].cpu()) and
+                      torch.equal(out_h["stress"][elo:ehi], out_d["stress"][elo:ehi].cpu()))
+            same = sum_over_ranks([0.0 if ok else 1.0])[0] == 0.0
+        else:
+            same = bool(torch.equal(out_h["ux"], out_d["ux"].cpu()) and torch.equal(out_h["stress"], out_d["stress"].cpu()))
+        if not same:
+            failures.append("the host-buffer step did not return the device-resident step's result bit for bit")
         e2e = {"value": E / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e_steps,
-               "host_result_bit_identical_to_device_step": same}
+               "host_result_bit_identical_to_device_step": same,
+               "scope": "every rank uploads 1/N of each input array (NVLink allgather after) and reads back its 1/N slice "
+                        "of the results" if world > 1 else "one rank: everything"}
 
     # ---- CPU baseline beside it ----------------------------------------------------------------
     cpu = None

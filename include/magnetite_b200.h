@@ -32,7 +32,8 @@
 extern "C" {
 #endif
 
-#define MAG_ABI_VERSION 3   /* 3: mag_options.assembly renumbered (0 = gather, now the default; 1 = sorted COO keys); mag_system_residual */
+#define MAG_ABI_VERSION 3   /* 3: mag_options.assembly renumbered (0 = gather, now the default; 1 = sorted COO keys), precond 3,
+                             *    result_scope; mag_stats.precond_used; mag_system_residual */
 
 /* src/solver.rs:17-19 */
 #define MAG_DOF 2
@@ -96,6 +97,10 @@ typedef struct {
                               * 1: the north star's wording — K_e per triangle, 9 COO keys per triangle, stable sort,
                               *    warp-shuffle segmented reduction.
                               * (ABI 2 had them the other way round: 0 sorted keys, 1 gather.) */
+    int32_t result_scope;    /* multi-GPU: 0 (default) every rank returns the complete result arrays; 1: a rank writes only
+                              * its slice of them — nodes [N*r/R, N*(r+1)/R) (mag_partition_nodes) and elements
+                              * [E*r/R, E*(r+1)/R) — so the job reads the result back over PCIe once, not once per rank */
+    int32_t reserved0;
     void *stream;            /* cudaStream_t to run on, or NULL for the ctx's own      */
 } mag_options;
 

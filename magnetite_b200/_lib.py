@@ -45,6 +45,7 @@ class MagOptions(C.Structure):
                 ("drop_exact_zeros", C.c_int32), ("check_every", C.c_int32),
                 ("spmv_format", C.c_int32), ("want_sigma", C.c_int32), ("allreduce", C.c_int32),
                 ("coarse_aggregates", C.c_int32), ("assembly", C.c_int32),
+                ("result_scope", C.c_int32), ("reserved0", C.c_int32),
                 ("stream", C.c_void_p)]
 
 

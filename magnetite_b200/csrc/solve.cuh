@@ -804,15 +804,25 @@ static void check_result_args(const mag_system *S, const mag_result *out) {
     if (S->n_elems && !out->stress) fail(MAG_ERR_BAD_ARG, "result: stress is required");
 }
 
-static void download_result(mag_ctx *ctx, const mag_system *S, PostBuffers &B, mag_result *out, bool want_sigma) {
+// scope 1 (multi-rank): only this rank's slice of every array — nodes by mag_partition_nodes, elements split evenly.
+static void download_result(mag_ctx *ctx, const mag_system *S, PostBuffers &B, mag_result *out, bool want_sigma,
+                            int scope = 0) {
     const size_t N = S->n_nodes, E = S->n_elems;
     const bool odev = out->on_device != 0;
-    copy_from_device(ctx, out->ux, (const double *)B.ux.p, N, odev);
-    copy_from_device(ctx, out->uy, (const double *)B.uy.p, N, odev);
-    copy_from_device(ctx, out->fx, (const double *)B.fx.p, N, odev);
-    copy_from_device(ctx, out->fy, (const double *)B.fy.p, N, odev);
-    copy_from_device(ctx, out->stress, (const double *)B.stress.p, E, odev);
-    if (want_sigma) copy_from_device(ctx, out->sigma, (const double *)B.sigma.p, E * 3, odev);
+    size_t n0 = 0, n1 = N, e0 = 0, e1 = E;
+    if (scope == 1 && S->nranks > 1) {
+        uint64_t lo, hi;
+        partition_nodes(N, S->nranks, S->rank, &lo, &hi);
+        n0 = lo; n1 = hi;
+        partition_nodes(E, S->nranks, S->rank, &lo, &hi);
+        e0 = lo; e1 = hi;
+    }
+    copy_from_device(ctx, out->ux + n0, (const double *)B.ux.p + n0, n1 - n0, odev);
+    copy_from_device(ctx, out->uy + n0, (const double *)B.uy.p + n0, n1 - n0, odev);
+    copy_from_device(ctx, out->fx + n0, (const double *)B.fx.p + n0, n1 - n0, odev);
+    copy_from_device(ctx, out->fy + n0, (const double *)B.fy.p + n0, n1 - n0, odev);
+    copy_from_device(ctx, out->stress + e0, (const double *)B.stress.p + e0, e1 - e0, odev);
+    if (want_sigma) copy_from_device(ctx, out->sigma + 3 * e0, (const double *)B.sigma.p + 3 * e0, (e1 - e0) * 3, odev);
 }
 
 static void raise_solver_status(const SolveOutcome &o, const mag_stats &st, bool compat = false) {
@@ -865,7 +875,8 @@ static void solve_impl(mag_system *S, const mag_options *opt_in, mag_result *out
     st.ms_post = phase.stop();
 
     phase.start();
-    download_result(ctx, S, B, out, want_sigma);
+    download_result(ctx, S, B, out, want_sigma, opt.result_scope);
+    MAG_CUDA(cudaStreamSynchronize(ctx->stream));
     st.ms_download = phase.stop();
     st.kernel_launches = ctx->launches - launches_before;
     S->stats.iters = st.iters;

@@ -49,6 +49,8 @@ pub mod sys {
         pub allreduce: i32,
         pub coarse_aggregates: i32,
         pub assembly: i32,
+        pub result_scope: i32,
+        pub reserved0: i32,
         pub stream: *mut c_void,
     }
     #[repr(C)]

@@ -37,7 +37,7 @@ def test_struct_layouts_match_header(built):
     # sizes computed by hand from include/magnetite_b200.h (LP64)
     assert C.sizeof(_lib.MagMesh) == 2 * 8 + 10 * 8 + 8
     assert C.sizeof(_lib.MagMaterial) == 24
-    assert C.sizeof(_lib.MagOptions) == 8 + 8 + 8 + 10 * 4 + 8
+    assert C.sizeof(_lib.MagOptions) == 8 + 8 + 8 + 12 * 4 + 8
     assert C.sizeof(_lib.MagResult) == 6 * 8 + 8
     o = _lib.default_options()
     assert (o.rel_tol, o.abs_tol, o.max_iter, o.precond, o.compat, o.drop_exact_zeros) == (1e-9, 1e-4, 10_000_000, 3, 0, 1)
