@@ -266,70 +266,105 @@ __global__ void coarse_fix_diagonal_kernel(double *__restrict__ band, uint32_t n
     if (k < nc && band[(size_t)k * (hb + 1)] == 0.0) band[(size_t)k * (hb + 1)] = 1.0;
 }
 
-// In-place banded Cholesky Ac = L L^T (right-looking), one CTA.  The rows j..j+hb that step j touches sit in a
-// circular shared-memory window win[(row % W)*W + k] = A[row][row-k], W = hb+1; row j leaves for global memory
-// when it is final and row j+W takes its slot (loaded into registers at the start of the step, so its latency
-// hides behind the step).  Two barriers per step.  *not_spd is set at the first non-positive pivot.
+// In-place banded Cholesky Ac = L L^T (right-looking), one CTA, THREE columns (one aggregate) per step.  The rows
+// j..j+hb+2 a step touches sit in a circular shared-memory window win[(row % R)*Wk + k] = A[row][row-k], R = hb+3 row
+// slots of Wk = hb+1 entries; the three rows that enter the window travel through registers during the step.
+// Two barriers per step.  The trailing update is bound by shared-memory bandwidth: with three columns at once every
+// window entry is read and written once per aggregate instead of once per column (8.8 -> see profiles).
+// n is a multiple of 3 (three modes per aggregate).  *not_spd is set at the first non-positive pivot.
 __global__ void __launch_bounds__(1024)
 band_cholesky_kernel(double *__restrict__ band, uint32_t n, uint32_t hb, double *__restrict__ invd,
                      int *__restrict__ not_spd) {
     extern __shared__ double chol_smem[];
-    const uint32_t W = hb + 1;
-    double *win = chol_smem;                    // W*W
-    double *colv = chol_smem + (size_t)W * W;   // W: column j below the diagonal, scaled
+    const uint32_t Wk = hb + 1, R = hb + 3;
+    double *win = chol_smem;                        // R * Wk
+    double *colv = chol_smem + (size_t)R * Wk;      // 3 * R: the three scaled columns, colv[c*R + p]
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
     const uint32_t tx = tid & 31u, ty = tid >> 5;                    // 32 x 32 threads for the trailing update
-    for (uint32_t e = tid; e < W * W; e += nt) {
-        const uint32_t row = e / W, k = e % W;
-        win[e] = row < n ? band[(size_t)row * W + k] : 0.0;
+    for (uint32_t e = tid; e < R * Wk; e += nt) {
+        const uint32_t row = e / Wk, k = e % Wk;
+        win[e] = row < n ? band[(size_t)row * Wk + k] : 0.0;
     }
     __syncthreads();
-    uint32_t slot_j = 0;                                             // j % W
-    for (uint32_t j = 0; j < n; ++j, slot_j = (slot_j + 1 == W) ? 0u : slot_j + 1) {
-        double *rowj = win + (size_t)slot_j * W;
-        // the row that enters the window after this step: on its way while the step runs (W <= 1024 threads)
+    uint32_t slot_j = 0;                                             // j % R
+    for (uint32_t j = 0; j < n; j += 3) {
+        // the rows that enter the window after this step: on their way while the step runs (3*Wk <= 1024 threads)
         double incoming = 0.0;
-        if (tid < W && j + W < n) incoming = band[(size_t)(j + W) * W + tid];
-        double d = rowj[0];                                          // every thread: the same pivot, the same bits
-        if (!(d > 0.0)) { if (tid == 0) *not_spd = 1; d = 1.0; }
-        const double rd = rsqrt(d);                                  // 1/sqrt(pivot); L[j][j] = pivot * rd
-        d *= rd;
-        const uint32_t pmax = min(hb, n - 1 - j);                    // rows j+1 .. j+pmax hold column j
-        for (uint32_t p = 1 + tid; p <= pmax; p += nt) {
+        {
+            const uint32_t rr = tid / Wk, k = tid % Wk;
+            if (rr < 3 && j + R + rr < n) incoming = band[(size_t)(j + R + rr) * Wk + k];
+        }
+        const uint32_t s0 = slot_j, s1 = (slot_j + 1 >= R) ? slot_j + 1 - R : slot_j + 1,
+                       s2 = (slot_j + 2 >= R) ? slot_j + 2 - R : slot_j + 2;
+        // 3 x 3 diagonal block, by every thread (the same bits everywhere)
+        const double a00 = win[(size_t)s0 * Wk], a10 = win[(size_t)s1 * Wk + 1], a11 = win[(size_t)s1 * Wk];
+        const double a20 = win[(size_t)s2 * Wk + 2], a21 = win[(size_t)s2 * Wk + 1], a22 = win[(size_t)s2 * Wk];
+        bool bad = !(a00 > 0.0);
+        const double r0 = rsqrt(bad ? 1.0 : a00), l00 = (bad ? 1.0 : a00) * r0;
+        const double l10 = a10 * r0, l20 = a20 * r0;
+        double d1 = a11 - l10 * l10;
+        if (!(d1 > 0.0)) { bad = true; d1 = 1.0; }
+        const double r1 = rsqrt(d1), l11 = d1 * r1;
+        const double l21 = (a21 - l20 * l10) * r1;
+        double d2 = a22 - l20 * l20 - l21 * l21;
+        if (!(d2 > 0.0)) { bad = true; d2 = 1.0; }
+        const double r2 = rsqrt(d2), l22 = d2 * r2;
+        if (bad && tid == 0) *not_spd = 1;
+        // panel: rows j+p, p = 3 .. pmax, hold (up to) three entries of the block column: k = p - c
+        const uint32_t pmax = min(hb + 2, n - 1 - j);
+        for (uint32_t p = 3 + tid; p <= pmax; p += nt) {
             uint32_t slot = slot_j + p;
-            if (slot >= W) slot -= W;
-            double *ri = win + (size_t)slot * W;
-            const double l = ri[p] * rd;
-            ri[p] = l;
-            colv[p] = l;
+            if (slot >= R) slot -= R;
+            double *ri = win + (size_t)slot * Wk;
+            const double x0 = p <= hb ? ri[p] : 0.0, x1 = p - 1 <= hb ? ri[p - 1] : 0.0, x2 = ri[p - 2];
+            const double m0 = x0 * r0;
+            const double m1 = (x1 - m0 * l10) * r1;
+            const double m2 = (x2 - m0 * l20 - m1 * l21) * r2;
+            if (p <= hb) ri[p] = m0;
+            if (p - 1 <= hb) ri[p - 1] = m1;
+            ri[p - 2] = m2;
+            colv[p] = m0; colv[R + p] = m1; colv[2 * R + p] = m2;
         }
         __syncthreads();
-        // row j is final (its diagonal is d, the rest was finished by earlier steps): store it and put row j+W into
-        // its slot — nothing below touches that slot before the barrier at the end of the step
-        if (tid == 0) invd[j] = rd;
-        if (tid < W) {
-            band[(size_t)j * W + tid] = tid ? rowj[tid] : d;
-            rowj[tid] = incoming;
+        // the three rows of the block are final: store them, and put rows j+R .. j+R+2 into their slots — nothing
+        // below touches those slots before the barrier at the end of the step
+        if (tid == 0) { invd[j] = r0; invd[j + 1] = r1; invd[j + 2] = r2; }
+        {
+            const uint32_t rr = tid / Wk, k = tid % Wk;
+            if (rr < 3) {
+                const uint32_t slot = rr == 0 ? s0 : (rr == 1 ? s1 : s2);
+                double v = win[(size_t)slot * Wk + k];
+                if (rr == 0 && k == 0) v = l00;
+                if (rr == 1) { if (k == 0) v = l11; else if (k == 1) v = l10; }
+                if (rr == 2) { if (k == 0) v = l22; else if (k == 1) v = l21; else if (k == 2) v = l20; }
+                band[(size_t)(j + rr) * Wk + k] = v;
+                win[(size_t)slot * Wk + k] = incoming;
+            }
         }
-        // trailing update: A[j+p][j+q] -= l_p * l_q for 1 <= q <= p <= pmax, in 32 x 32 tiles of (p, q)
-        // (the step is bound by shared-memory traffic: the l_q a thread needs are the same for all its p — registers)
-        double lq[5];
+        // trailing update: A[j+p][j+q] -= sum_c l_pc * l_qc for 3 <= q <= p <= pmax, in 32 x 32 tiles of (p, q)
+        double lq0[5], lq1[5], lq2[5];
 #pragma unroll
-        for (int u = 0; u < 5; ++u) { const uint32_t q = tx + 1 + 32u * u; lq[u] = q <= pmax ? colv[q] : 0.0; }
-        for (uint32_t p0 = 0; p0 < pmax; p0 += 32) {
-            const uint32_t p = p0 + ty + 1;
+        for (int u = 0; u < 5; ++u) {
+            const uint32_t q = tx + 3 + 32u * u;
+            const bool ok = q <= pmax;
+            lq0[u] = ok ? colv[q] : 0.0; lq1[u] = ok ? colv[R + q] : 0.0; lq2[u] = ok ? colv[2 * R + q] : 0.0;
+        }
+        for (uint32_t p0 = 3; p0 <= pmax; p0 += 32) {
+            const uint32_t p = p0 + ty;
             if (p > pmax) break;
             uint32_t slot = slot_j + p;
-            if (slot >= W) slot -= W;
-            double *rp = win + (size_t)slot * W;
-            const double lp = colv[p];
+            if (slot >= R) slot -= R;
+            double *rp = win + (size_t)slot * Wk;
+            const double lp0 = colv[p], lp1 = colv[R + p], lp2 = colv[2 * R + p];
 #pragma unroll
             for (int u = 0; u < 5; ++u) {
-                const uint32_t q = tx + 1 + 32u * u;
-                if (q <= p) rp[p - q] -= lp * lq[u];
+                const uint32_t q = tx + 3 + 32u * u;
+                if (q <= p) rp[p - q] -= lp0 * lq0[u] + lp1 * lq1[u] + lp2 * lq2[u];
             }
         }
         __syncthreads();
+        slot_j += 3;
+        if (slot_j >= R) slot_j -= R;
     }
 }
 

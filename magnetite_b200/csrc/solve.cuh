@@ -499,7 +499,7 @@ static bool setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
         MAG_LAUNCH(ctx, coarse_band_kernel, C.n_agg, 96, 0, (const double *)C.Ac_compact.p, C.grid, hb, lower.p);
         C.Ac_compact.release();
         MAG_LAUNCH(ctx, coarse_fix_diagonal_kernel, cdiv(nc, 256), 256, 0, lower.p, nc, hb);
-        const size_t chol_smem = ((size_t)Wb * Wb + Wb) * sizeof(double);
+        const size_t chol_smem = ((size_t)(hb + 3) * Wb + 3 * (size_t)(hb + 3)) * sizeof(double);
         if (chol_smem > 200 * 1024) fail(MAG_ERR_BAD_ARG, "two-level preconditioner: band of %u does not fit the factorisation window", hb);
         MAG_CUDA(cudaFuncSetAttribute(band_cholesky_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
         MAG_LAUNCH(ctx, band_cholesky_kernel, 1, 1024, chol_smem, lower.p, nc, hb, invd.p, bad.p);
