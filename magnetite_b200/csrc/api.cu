@@ -652,6 +652,7 @@ extern "C" int mag_comm_init(mag_ctx *ctx, int rank, int nranks, const void *id1
     return guarded([&] {
         if (!ctx || !id128 || nranks <= 0 || rank < 0 || rank >= nranks) fail(MAG_ERR_BAD_ARG, "bad communicator request");
         if (ctx->comm) fail(MAG_ERR_BAD_ARG, "the context already has a communicator");
+        if (nranks > kMaxRanks) fail(MAG_ERR_BAD_ARG, "at most %d ranks (mailboxes and push segments are sized for one NVSwitch box)", kMaxRanks);
         MAG_CUDA(cudaSetDevice(ctx->device));
         ncclUniqueId id;
         std::memcpy(&id, id128, sizeof id);

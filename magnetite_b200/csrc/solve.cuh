@@ -363,6 +363,7 @@ static bool setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
     const int R = ranks.size() > 1 ? (int)ranks.size() : ranks[0].S->nranks;
     std::vector<double *> mats;
     std::vector<std::vector<uint8_t>> has_rows(ranks.size()), need(ranks.size());
+    bool any_far = false;
     for (size_t q = 0; q < ranks.size(); ++q) {
         RankState &W = ranks[q];
         mag_system *S = W.S;
@@ -450,8 +451,7 @@ static bool setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
         int h_far = 0;
         MAG_CUDA(cudaMemcpyAsync(&h_far, far.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         MAG_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (h_far) fail(MAG_ERR_BAD_ARG, "two-level preconditioner: an element spans non-adjacent aggregates "
-                                          "(%u x %u boxes are too small for this mesh); lower coarse_aggregates", g.nbx, g.nby);
+        if (h_far) any_far = true;       // an element spans non-adjacent boxes: this grid cannot carry the 9-point coarse stencil
         C.y.alloc(ctx, C.nc); C.w.alloc(ctx, C.nc);
         C.y.zero(); C.w.zero();
         C.partials.alloc(ctx, 2 * (size_t)ctx->sm_count * 8);
@@ -462,6 +462,15 @@ static bool setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
     }
     reduce_vector(ctx, ranks, m, mats, (size_t)ranks[0].S->coarse.n_agg * 81);      // block rows, summed over ranks
     lap("sum over ranks");
+    {
+        // boxes smaller than an element somewhere (on any rank): no coarse space, the caller runs Jacobi
+        std::vector<std::vector<uint8_t>> flag(ranks.size(), std::vector<uint8_t>(1, any_far ? 1 : 0));
+        for (const auto &f : exchange_bytes(ctx, ranks, flag, 1)) any_far = any_far || f[0];
+        if (any_far) {
+            for (RankState &W : ranks) { W.S->coarse.failed = true; W.S->coarse.ready = false; }
+            return false;
+        }
+    }
     const uint32_t n_agg = ranks[0].S->coarse.n_agg;
     const std::vector<std::vector<uint8_t>> all_has = exchange_bytes(ctx, ranks, has_rows, n_agg);
     std::vector<uint16_t> touch(n_agg, 0);
@@ -614,6 +623,9 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
     PcgScalars &hs = out.hs;
     const uint32_t n_glob = ranks[0].S->n_free;
     if (n_glob == 0) { hs.stop = 1; return out; }
+    // the sequence number of a peer message carries iteration + 1 in 24 bits (pcg.cuh: ll_seq)
+    if (opt.max_iter >= (1ull << 24) - 2 && (ranks.size() > 1 || ranks[0].S->nranks > 1))
+        fail(MAG_ERR_BAD_ARG, "multi-GPU solves take max_iter < 2^24 - 2 (got %llu)", (unsigned long long)opt.max_iter);
     // one rank, no coarse space, small enough for one cluster's shared memory: the single-kernel solve
     if (ranks.size() == 1 && ranks[0].S->nranks == 1 && !mode.two_level && mode.format != 1 &&
         small_cg_try(ctx, ranks[0], opt, jacobi, compat, out))

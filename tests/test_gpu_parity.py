@@ -461,6 +461,9 @@ def test_two_level_on_examples_and_indefinite_meshes(ctx):
     fb = solver.solve_soa(golden_mesh(t), META.__class__(*t["material"]), ctx, _lib.default_options(rel_tol=1e-13, precond=2))
     assert fb.stats["precond_used"] == 1 and fb.stats["converged"] == 1 and fb.stats["negative_definite"] == 1
     assert rel_l2(np.concatenate([fb.ux, fb.uy]), np.concatenate([t["ux"], t["uy"]])) < 1e-9
+    # boxes smaller than the elements (2048 aggregates on an 800-cell plate): no 9-point coarse stencil, Jacobi again
+    fine = solver.solve_soa(meshgen.plate(40, 20), META, ctx, _lib.default_options(precond=2, coarse_aggregates=2048))
+    assert fine.stats["precond_used"] == 1 and fine.stats["converged"] == 1
     # the default (precond 3 = auto): Jacobi below 20 000 unknowns, two-level above
     small = solver.solve_soa(meshgen.plate(40, 20), META, ctx, _lib.default_options())
     large = solver.solve_soa(meshgen.plate(160, 80), META, ctx, _lib.default_options())
