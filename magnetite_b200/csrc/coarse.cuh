@@ -383,8 +383,9 @@ __global__ void band_transpose_kernel(const double *__restrict__ lower, uint32_t
 // kInvChunk rows, the next chunk prefetched through registers while the current one is used).  The last hb
 // entries of a warp's vector live in REGISTERS, systolically: lane l, group g holds z_{i-1-l-32g}; after a step
 // every value moves one lane up (shuffle) and the new entry enters at lane 0.
-constexpr int kInvWarps = 16, kInvChunk = 32, kInvGroups = 5;        // 5 x 32 = 160 >= hb (<= 3*46+2 = 140)
+constexpr int kInvChunk = 32, kInvGroups = 5;                       // 5 x 32 = 160 >= hb (<= 3*46+2 = 140)
 constexpr uint32_t kInvMaxBand = 32 * kInvGroups;
+template <int kInvWarps>              // 16: many right-hand sides (fewer CTAs read the factor); 8: few (shorter steps)
 __global__ void __launch_bounds__(kInvWarps * 32)
 band_inverse_rows_kernel(const double *__restrict__ lower, const double *__restrict__ upper,
                          const double *__restrict__ invd, uint32_t n, uint32_t hb,
@@ -398,18 +399,18 @@ band_inverse_rows_kernel(const double *__restrict__ lower, const double *__restr
     const uint32_t c = live ? crow[r] : 0xffffffffu;
     double *orow = out + (size_t)(live ? r : 0) * n;
     const uint32_t c_first = crow[blockIdx.x * kInvWarps];           // crow ascends: nothing happens before this row
-    const uint32_t per_thread = (kInvChunk * W + blockDim.x - 1) / blockDim.x;   // <= 32*141/512 = 9
-    double stash[9];
+    const uint32_t per_thread = (kInvChunk * W + blockDim.x - 1) / blockDim.x;   // <= 32*141/(32*kInvWarps)
+    double stash[18];                                               // kInvChunk*W / (32*kInvWarps) <= 32*141/256
     auto fetch = [&](const double *src, uint32_t row0, uint32_t nrows) {          // global -> registers
 #pragma unroll
-        for (uint32_t u = 0; u < 9; ++u) {
+        for (uint32_t u = 0; u < 144 / kInvWarps; ++u) {
             const uint32_t e = threadIdx.x + u * blockDim.x;
             stash[u] = (u < per_thread && e < nrows * W) ? src[(size_t)row0 * W + e] : 0.0;
         }
     };
     auto commit = [&](double *dst, uint32_t nrows) {                              // registers -> shared
 #pragma unroll
-        for (uint32_t u = 0; u < 9; ++u) {
+        for (uint32_t u = 0; u < 144 / kInvWarps; ++u) {
             const uint32_t e = threadIdx.x + u * blockDim.x;
             if (u < per_thread && e < nrows * W) dst[e] = stash[u];
         }
@@ -599,12 +600,14 @@ coarse_apply_kernel(const double *__restrict__ Ainv, const uint32_t *__restrict_
         const double *a = Ainv + (size_t)i * nc;
         double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
         uint32_t c = threadIdx.x;
-        for (; c + 768 < nc; c += 1024) {
-            const double a0 = __ldcs(a + c), a1 = __ldcs(a + c + 256), a2 = __ldcs(a + c + 512), a3 = __ldcs(a + c + 768);
-            acc0 = fma(a0, __ldg(w + c), acc0);
-            acc1 = fma(a1, __ldg(w + c + 256), acc1);
-            acc2 = fma(a2, __ldg(w + c + 512), acc2);
-            acc3 = fma(a3, __ldg(w + c + 768), acc3);
+        for (; c + 1792 < nc; c += 2048) {                           // eight loads in flight per thread
+            double av[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) av[u] = __ldcs(a + c + 256 * u);
+            acc0 = fma(av[0], __ldg(w + c), acc0);           acc1 = fma(av[1], __ldg(w + c + 256), acc1);
+            acc2 = fma(av[2], __ldg(w + c + 512), acc2);     acc3 = fma(av[3], __ldg(w + c + 768), acc3);
+            acc0 = fma(av[4], __ldg(w + c + 1024), acc0);    acc1 = fma(av[5], __ldg(w + c + 1280), acc1);
+            acc2 = fma(av[6], __ldg(w + c + 1536), acc2);    acc3 = fma(av[7], __ldg(w + c + 1792), acc3);
         }
         for (; c < nc; c += 256) acc0 = fma(__ldcs(a + c), __ldg(w + c), acc0);
         double acc = (acc0 + acc1) + (acc2 + acc3);

@@ -522,9 +522,16 @@ static bool setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
         if (C.m) {
             if (hb > kInvMaxBand) fail(MAG_ERR_BAD_ARG, "two-level preconditioner: band of %u exceeds the substitution kernel's %u", hb, kInvMaxBand);
             const size_t inv_smem = 2 * (size_t)kInvChunk * Wb * sizeof(double);
-            MAG_CUDA(cudaFuncSetAttribute(band_inverse_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem));
-            MAG_LAUNCH(ctx, band_inverse_rows_kernel, cdiv(C.m, kInvWarps), kInvWarps * 32, inv_smem, (const double *)lower.p,
-                       (const double *)upper.p, (const double *)invd.p, nc, hb, (const uint32_t *)C.crow.p, C.m, C.Ainv.p);
+            // few right-hand sides (a rank of a multi-GPU run): 8 warps per CTA — twice the CTAs, shorter steps
+            if (C.m <= (uint32_t)ctx->sm_count * 8u) {
+                MAG_CUDA(cudaFuncSetAttribute(band_inverse_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem));
+                MAG_LAUNCH(ctx, band_inverse_rows_kernel<8>, cdiv(C.m, 8), 8 * 32, inv_smem, (const double *)lower.p,
+                           (const double *)upper.p, (const double *)invd.p, nc, hb, (const uint32_t *)C.crow.p, C.m, C.Ainv.p);
+            } else {
+                MAG_CUDA(cudaFuncSetAttribute(band_inverse_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inv_smem));
+                MAG_LAUNCH(ctx, band_inverse_rows_kernel<16>, cdiv(C.m, 16), 16 * 32, inv_smem, (const double *)lower.p,
+                           (const double *)upper.p, (const double *)invd.p, nc, hb, (const uint32_t *)C.crow.p, C.m, C.Ainv.p);
+            }
         }
         // single rank without a shared slab: its own buffer for the partial restrictions
         if (!S->shared_slab) {
