@@ -71,9 +71,11 @@ struct CoarseSpace {
     uint32_t n_agg = 0, nc = 0, hb = 0;
     uint32_t n_lagg = 0, m = 0;
     DevBuf<uint32_t> mode;        // per GLOBAL reduced column: 3*aggregate + axis
-    DevBuf<double> rot;           // per GLOBAL reduced column: rotation-mode coefficient
+    DevBuf<float> rot;            // per GLOBAL reduced column: rotation-mode coefficient.  fp32 on purpose: P is DEFINED by
+                                  // these numbers (restriction, prolongation and Galerkin product read the same ones), so
+                                  // their precision costs nothing but 4 bytes per row in two kernels of every iteration
     DevBuf<uint32_t> perm_ax;     // local rows sorted by aggregate: (row << 2) | axis
-    DevBuf<double> rot_perm;      // rot of those rows, in that order
+    DevBuf<float> rot_perm;       // rot of those rows, in that order
     DevBuf<uint32_t> agg_ptr;     // n_agg+1 segment starts into perm_ax
     DevBuf<uint32_t> lagg;        // the aggregates that have local rows
     DevBuf<uint32_t> crow;        // coarse unknowns whose row of Ac^-1 this rank applies, ascending (m)
@@ -121,7 +123,7 @@ __global__ void bbox_kernel(const double2 *__restrict__ xy, size_t n, double *__
 // For every DOF with an unknown displacement: mode / rot of its reduced column.
 __global__ void coarse_colinfo_kernel(const double2 *__restrict__ xy, const uint8_t *__restrict__ known,
                                       const uint32_t *__restrict__ colmap, size_t n_dof, CoarseGrid g,
-                                      uint32_t *__restrict__ mode, double *__restrict__ rot) {
+                                      uint32_t *__restrict__ mode, float *__restrict__ rot) {
     const size_t d = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n_dof) return;
     const uint32_t node = (uint32_t)(d >> 1), ax = (uint32_t)(d & 1);
@@ -133,7 +135,7 @@ __global__ void coarse_colinfo_kernel(const double2 *__restrict__ xy, const uint
     const double xc = g.x0 + ((double)bx + 0.5) * g.hx, yc = g.y0 + ((double)by + 0.5) * g.hy;
     const uint32_t c = colmap[d];
     mode[c] = 3u * agg + ax;
-    rot[c] = ax ? (p.x - xc) / g.hx : -(p.y - yc) / g.hy;
+    rot[c] = (float)(ax ? (p.x - xc) / g.hx : -(p.y - yc) / g.hy);
 }
 
 __global__ void coarse_rowkeys_kernel(const uint32_t *__restrict__ mode, uint32_t n_rows, uint32_t row_lo,
@@ -159,8 +161,8 @@ __global__ void coarse_segments_kernel(const uint64_t *__restrict__ keys, uint32
 
 // rows in aggregate order with everything the restriction needs next to them: (row << 2) | axis and rot
 __global__ void coarse_pack_rows_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ mode,
-                                        const double *__restrict__ rot, uint32_t n_rows, uint32_t row_lo,
-                                        uint32_t *__restrict__ perm_ax, double *__restrict__ rot_perm) {
+                                        const float *__restrict__ rot, uint32_t n_rows, uint32_t row_lo,
+                                        uint32_t *__restrict__ perm_ax, float *__restrict__ rot_perm) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_rows) return;
     const uint32_t row = perm[s], g = row_lo + row;
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(kGalerkinWarps * 32)
 coarse_galerkin_kernel(const uint32_t *__restrict__ agg_ptr, const uint32_t *__restrict__ perm_ax,
                        const uint32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                        const double *__restrict__ val, const uint32_t *__restrict__ mode,
-                       const double *__restrict__ rot, uint32_t row_lo, CoarseGrid g,
+                       const float *__restrict__ rot, uint32_t row_lo, CoarseGrid g,
                        double *__restrict__ Ac, int *__restrict__ far) {
     __shared__ double part[kGalerkinWarps][81];
     const uint32_t I = blockIdx.x;
@@ -199,7 +201,7 @@ coarse_galerkin_kernel(const uint32_t *__restrict__ agg_ptr, const uint32_t *__r
     for (uint32_t s = agg_ptr[I] + warp; s < agg_ptr[I + 1]; s += kGalerkinWarps) {
         const uint32_t pa = perm_ax[s], i = pa >> 2;
         const int axi = (int)(pa & 3u);
-        const double roti = rot[row_lo + i];
+        const double roti = (double)rot[row_lo + i];
         const uint32_t e0 = rowptr[i], e1 = rowptr[i + 1];
         double t = 0.0;
         for (uint32_t base = e0; base < e1; base += 32) {
@@ -209,7 +211,7 @@ coarse_galerkin_kernel(const uint32_t *__restrict__ agg_ptr, const uint32_t *__r
             if (e < e1) {
                 const uint32_t c = (uint32_t)col[e];
                 const uint32_t mj = mode[c];
-                v = val[e]; rc = rot[c];
+                v = val[e]; rc = (double)rot[c];
                 axj = (int)(mj % 3u);
                 int cx, cy;
                 g.coords(mj / 3u, cx, cy);
@@ -511,7 +513,7 @@ band_inverse_rows_kernel(const double *__restrict__ lower, const double *__restr
 constexpr int kRestrictThreads = 512;
 __global__ void __launch_bounds__(kRestrictThreads)
 coarse_restrict_kernel(const uint32_t *__restrict__ lagg, const uint32_t *__restrict__ agg_ptr,
-                       const uint32_t *__restrict__ perm_ax, const double *__restrict__ rot_perm,
+                       const uint32_t *__restrict__ perm_ax, const float *__restrict__ rot_perm,
                        const double *__restrict__ r, uint32_t row_lo, int step, CoarseLinks links,
                        const PcgScalars *__restrict__ sc) {
     if (sc->stop) return;
@@ -525,7 +527,7 @@ coarse_restrict_kernel(const uint32_t *__restrict__ lagg, const uint32_t *__rest
         for (int u = 0; u < 4; ++u) {
             const uint32_t su = s + u * kRestrictThreads;
             pa[u] = su < s1 ? perm_ax[su] : 0xffffffffu;
-            tq[u] = su < s1 ? rot_perm[su] : 0.0;
+            tq[u] = su < s1 ? (double)rot_perm[su] : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) rq[u] = pa[u] != 0xffffffffu ? r[row_lo + (pa[u] >> 2)] : 0.0;

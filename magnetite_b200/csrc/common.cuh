@@ -64,7 +64,6 @@ class DeviceHeap {
 public:
     void *alloc(size_t bytes);
     void release(void *p);
-    void shrink(void *p, size_t bytes);     // keep the first `bytes` of a block, give the rest back
     void destroy();
     size_t reserved() const { return reserved_; }
 private:
@@ -89,7 +88,6 @@ struct mag_ctx {
     int tune = 0;                       // MAG_TUNE debug switches (see PcgScalars::tune)
     bool rs_attr_set = false;           // radix sort (64-bit keys): dynamic shared memory opt-in done on this device
     bool rs32_attr_set = false;         // same, 32-bit keys
-    bool fused_attr_set = false;        // fused assembly kernels: dynamic shared memory opt-in
     mag::Comm *comm = nullptr;
     // pinned host scratch for scalar read-backs
     double *h_scal = nullptr;
@@ -159,19 +157,6 @@ inline void DeviceHeap::release(void *ptr) {
     free_[p] = size;
 }
 
-inline void DeviceHeap::shrink(void *ptr, size_t bytes) {
-    char *p = static_cast<char *>(ptr);
-    auto u = used_.find(p);
-    if (u == used_.end()) return;
-    bytes = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
-    if (bytes >= u->second) return;
-    const size_t rest = u->second - bytes;
-    u->second = bytes;
-    char *tail = p + bytes;
-    used_[tail] = rest;          // hand the tail to release(): it coalesces with its free neighbours
-    release(tail);
-}
-
 inline void DeviceHeap::destroy() {
     for (const Slab &s : slabs_) cudaFree(s.base);
     slabs_.clear(); free_.clear(); used_.clear(); reserved_ = 0;
@@ -200,9 +185,6 @@ struct DevBuf {
     void zero() { if (p) MAG_CUDA(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), ctx->stream)); }
     void release() {
         if (p) { ctx->heap.release(p); p = nullptr; n = 0; }
-    }
-    void shrink(size_t count) {     // keeps the first `count` elements
-        if (p && count < n) { ctx->heap.shrink(p, (count ? count : 1) * sizeof(T)); n = count; }
     }
     ~DevBuf() { release(); }
     size_t bytes() const { return n * sizeof(T); }

@@ -296,11 +296,11 @@ pcg_update_xr_kernel(double *__restrict__ x, double *__restrict__ r, const doubl
 // Two-level preconditioner as seen by the p-update: z = Dinv r + P y (coarse.cuh); mode == null: off.
 struct CoarseView {
     const uint32_t *mode = nullptr;   // per global reduced row: 3*aggregate + axis
-    const double *rot = nullptr;      // rotation-mode coefficient
+    const float *rot = nullptr;       // rotation-mode coefficient (fp32: see CoarseSpace::rot)
     const double *y = nullptr;        // Ac^-1 P^T r
     __device__ __forceinline__ double prolong(uint32_t gi) const {
         const uint32_t m = mode[gi];
-        return __ldg(y + m) + rot[gi] * __ldg(y + (m - m % 3u) + 2u);
+        return __ldg(y + m) + (double)rot[gi] * __ldg(y + (m - m % 3u) + 2u);
     }
 };
 

@@ -271,7 +271,7 @@ static void enqueue_coarse_solve(mag_ctx *ctx, std::vector<RankState> &ranks, co
         CoarseSpace &C = W.S->coarse;
         if (C.n_lagg)
             MAG_LAUNCH(ctx, coarse_restrict_kernel, C.n_lagg, kRestrictThreads, 0, (const uint32_t *)C.lagg.p,
-                       (const uint32_t *)C.agg_ptr.p, (const uint32_t *)C.perm_ax.p, (const double *)C.rot_perm.p,
+                       (const uint32_t *)C.agg_ptr.p, (const uint32_t *)C.perm_ax.p, (const float *)C.rot_perm.p,
                        (const double *)W.r_ext, W.S->row_lo, step, C.links, (const PcgScalars *)W.scal.p);
     }
     const bool local_sum = m.reduce == Reduce::kNccl || m.reduce == Reduce::kEmulated;
@@ -413,7 +413,7 @@ static bool setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
                            keys.p, perm.p);
                 radix_sort_pairs(ctx, keys.p, perm.p, keys_alt.p, pay_alt.p, n, bits_for((uint64_t)C.n_agg + 1));
                 MAG_LAUNCH(ctx, coarse_pack_rows_kernel, cdiv(n, 256), 256, 0, (const uint32_t *)perm.p,
-                           (const uint32_t *)C.mode.p, (const double *)C.rot.p, n, S->row_lo, C.perm_ax.p, C.rot_perm.p);
+                           (const uint32_t *)C.mode.p, (const float *)C.rot.p, n, S->row_lo, C.perm_ax.p, C.rot_perm.p);
             }
             MAG_LAUNCH(ctx, coarse_segments_kernel, cdiv((size_t)C.n_agg + 1, 256), 256, 0, (const uint64_t *)keys.p, n,
                        C.n_agg, C.agg_ptr.p);
@@ -447,7 +447,7 @@ static bool setup_coarse(mag_ctx *ctx, std::vector<RankState> &ranks, const Solv
         far.zero();
         MAG_LAUNCH(ctx, coarse_galerkin_kernel, C.n_agg, kGalerkinWarps * 32, 0, (const uint32_t *)C.agg_ptr.p, (const uint32_t *)C.perm_ax.p,
                    (const uint32_t *)S->Kff.rowptr.p, (const int32_t *)S->Kff.col.p, (const double *)S->Kff.val.p,
-                   (const uint32_t *)C.mode.p, (const double *)C.rot.p, S->row_lo, g, C.Ac_compact.p, far.p);
+                   (const uint32_t *)C.mode.p, (const float *)C.rot.p, S->row_lo, g, C.Ac_compact.p, far.p);
         int h_far = 0;
         MAG_CUDA(cudaMemcpyAsync(&h_far, far.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         MAG_CUDA(cudaStreamSynchronize(ctx->stream));
