@@ -516,6 +516,7 @@ coarse_restrict_kernel(const uint32_t *__restrict__ lagg, const uint32_t *__rest
                        const uint32_t *__restrict__ perm_ax, const float *__restrict__ rot_perm,
                        const double *__restrict__ r, uint32_t row_lo, int step, CoarseLinks links,
                        const PcgScalars *__restrict__ sc) {
+    pdl_wait();
     if (sc->stop) return;
     const uint32_t I = lagg[blockIdx.x];
     double a[3] = {0.0, 0.0, 0.0};
@@ -569,6 +570,7 @@ coarse_restrict_kernel(const uint32_t *__restrict__ lagg, const uint32_t *__rest
 __global__ void __launch_bounds__(256)
 coarse_gather_w_kernel(const uint16_t *__restrict__ touch, uint32_t nc, int step, CoarseLinks clinks,
                        double *__restrict__ w, PcgScalars *sc) {
+    pdl_wait();
     if (sc->stop) return;
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nc) return;
@@ -594,6 +596,7 @@ coarse_apply_kernel(const double *__restrict__ Ainv, const uint32_t *__restrict_
                     const uint8_t *__restrict__ wy_mine, const double *__restrict__ w, uint32_t m, uint32_t nc,
                     int step, PeerLinks links, double *__restrict__ y, double *__restrict__ partials,
                     unsigned *__restrict__ ticket, PcgScalars *sc, double *__restrict__ wy_out) {
+    pdl_wait();
     if (sc->stop) return;
     __shared__ double red[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -645,6 +648,7 @@ coarse_apply_warp_kernel(const double *__restrict__ Ainv, const uint32_t *__rest
                          const uint8_t *__restrict__ wy_mine, const double *__restrict__ w, uint32_t m, uint32_t nc,
                          int step, PeerLinks links, double *__restrict__ y, double *__restrict__ partials,
                          unsigned *__restrict__ ticket, PcgScalars *sc, double *__restrict__ wy_out) {
+    pdl_wait();
     if (sc->stop) return;
     const int lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;

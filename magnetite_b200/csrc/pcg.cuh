@@ -212,6 +212,7 @@ pcg_spmv_kernel(const uint32_t *__restrict__ slice_off, const IDX *__restrict__ 
                 double *__restrict__ q, uint32_t n_rows, uint32_t n_slices, uint32_t row_lo,
                 int step, PeerLinks links, double *__restrict__ partials, PcgScalars *sc,
                 double *pq_out) {
+    pdl_wait();
     if (sc->stop) return;
     prof_start(sc, 0);
     const int parity = step & 1;
@@ -232,6 +233,7 @@ pcg_spmv_csr_kernel(const uint32_t *__restrict__ rowptr, const int32_t *__restri
                     const double *__restrict__ val, const double *__restrict__ p,
                     double *__restrict__ q, uint32_t n_rows, uint32_t row_lo, int step,
                     PeerLinks links, double *__restrict__ partials, PcgScalars *sc, double *pq_out) {
+    pdl_wait();
     if (sc->stop) return;
     prof_start(sc, 0);
     const int parity = step & 1;
@@ -260,6 +262,7 @@ pcg_update_xr_kernel(double *__restrict__ x, double *__restrict__ r, const doubl
                      const double *__restrict__ q, const double *__restrict__ dinv, uint32_t n,
                      uint32_t row_lo, int step, PushSegs push, PeerLinks links,
                      double *__restrict__ partials, PcgScalars *sc, double *pair_out) {
+    pdl_wait();
     if (sc->stop) return;
     prof_start(sc, 2);
     const int parity = step & 1;
@@ -310,6 +313,7 @@ __global__ void __launch_bounds__(256)
 pcg_update_p_kernel(double *__restrict__ p, const double *__restrict__ r,
                     const double *__restrict__ dinv, uint32_t ext_lo, uint32_t ext_hi, int step,
                     HaloView halo, CoarseView cv, PeerLinks links, PcgScalars *sc) {
+    pdl_wait();
     if (sc->stop) return;
     prof_start(sc, 5);
     const int parity = step & 1;
@@ -358,6 +362,7 @@ pcg_update_p_kernel(double *__restrict__ p, const double *__restrict__ r,
 
 // Last node of every graph launch: the next launch continues the iteration numbering.
 __global__ void pcg_chunk_end_kernel(int chunk, PcgScalars *sc) {
+    pdl_wait();
     if (!sc->stop) sc->chunk_base += (unsigned long long)chunk;
 }
 

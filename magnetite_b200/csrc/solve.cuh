@@ -207,6 +207,7 @@ struct SolveMode {
     Reduce reduce = Reduce::kNone;
     int format = 2;
     bool two_level = false;
+    bool pdl = true;          // programmatic dependent launches between the kernels of the loop (MAG_TUNE=512: off)
 };
 
 inline CoarseView coarse_view(RankState &W, const SolveMode &m) {
@@ -227,8 +228,7 @@ inline double *pair_target(RankState &W, const SolveMode &m, int slot) {
                                                                                       : kOffPair0 + 2 * (size_t)slot);
 }
 inline PeerLinks links_of(RankState &W, const SolveMode &m) {
-    PeerLinks none;
-    none.n = 0; none.me = 0;
+    PeerLinks none = {};
     return m.reduce == Reduce::kMailbox ? W.S->links : none;
 }
 
@@ -270,25 +270,25 @@ static void enqueue_coarse_solve(mag_ctx *ctx, std::vector<RankState> &ranks, co
     for (RankState &W : ranks) {
         CoarseSpace &C = W.S->coarse;
         if (C.n_lagg)
-            MAG_LAUNCH(ctx, coarse_restrict_kernel, C.n_lagg, kRestrictThreads, 0, (const uint32_t *)C.lagg.p,
+            MAG_LAUNCH_DEP(ctx, m.pdl, coarse_restrict_kernel, C.n_lagg, kRestrictThreads, 0, (const uint32_t *)C.lagg.p,
                        (const uint32_t *)C.agg_ptr.p, (const uint32_t *)C.perm_ax.p, (const float *)C.rot_perm.p,
                        (const double *)W.r_ext, W.S->row_lo, step, C.links, (const PcgScalars *)W.scal.p);
     }
     const bool local_sum = m.reduce == Reduce::kNccl || m.reduce == Reduce::kEmulated;
     for (RankState &W : ranks) {
         CoarseSpace &C = W.S->coarse;
-        MAG_LAUNCH(ctx, coarse_gather_w_kernel, cdiv(C.nc, 256), 256, 0, (const uint16_t *)C.touch.p, C.nc, step, C.links,
+        MAG_LAUNCH_DEP(ctx, m.pdl, coarse_gather_w_kernel, cdiv(C.nc, 256), 256, 0, (const uint16_t *)C.touch.p, C.nc, step, C.links,
                    C.w.p, W.scal.p);
         // enough rows to fill the machine with one warp each (a single GPU): warp per row; else a CTA per row
         const unsigned warp_ctas = cdiv((size_t)C.m * 32, 256);
         if (warp_ctas >= (unsigned)ctx->sm_count * 4u) {
-            MAG_LAUNCH(ctx, coarse_apply_warp_kernel, std::min(warp_ctas, (unsigned)ctx->sm_count * 8u), 256, 0,
+            MAG_LAUNCH_DEP(ctx, m.pdl, coarse_apply_warp_kernel, std::min(warp_ctas, (unsigned)ctx->sm_count * 8u), 256, 0,
                        (const double *)C.Ainv.p, (const uint32_t *)C.crow.p, (const uint8_t *)C.wy_mine.p,
                        (const double *)C.w.p, C.m, C.nc, step, links_of(W, m), C.y.p, C.partials.p, C.ticket.p,
                        W.scal.p, scal_field(W, local_sum ? kOffLocWy : kOffWy));
         } else {
             const unsigned grid = std::max(1u, std::min(C.m, (unsigned)ctx->sm_count * 8u));
-            MAG_LAUNCH(ctx, coarse_apply_kernel, grid, 256, 0, (const double *)C.Ainv.p, (const uint32_t *)C.crow.p,
+            MAG_LAUNCH_DEP(ctx, m.pdl, coarse_apply_kernel, grid, 256, 0, (const double *)C.Ainv.p, (const uint32_t *)C.crow.p,
                        (const uint8_t *)C.wy_mine.p, (const double *)C.w.p, C.m, C.nc, step, links_of(W, m), C.y.p,
                        C.partials.p, C.ticket.p, W.scal.p, scal_field(W, local_sum ? kOffLocWy : kOffWy));
         }
@@ -302,27 +302,27 @@ static void enqueue_iteration(mag_ctx *ctx, std::vector<RankState> &ranks, int s
         const SellMatrix &L = W.S->sell;
         const CsrMatrix &A = W.S->Kff;
         if (m.format == 1)
-            MAG_LAUNCH(ctx, pcg_spmv_csr_kernel, W.grid_vec, 256, 0, (const uint32_t *)A.rowptr.p,
+            MAG_LAUNCH_DEP(ctx, m.pdl, pcg_spmv_csr_kernel, W.grid_vec, 256, 0, (const uint32_t *)A.rowptr.p,
                        (const int32_t *)A.col.p, (const double *)A.val.p, (const double *)W.p_ext.p, W.q.p,
                        W.n, A.row_lo, step, links_of(W, m), W.partials.p, W.scal.p, pq_target(W, m));
         else if (L.narrow)
-            MAG_LAUNCH(ctx, pcg_spmv_kernel<int16_t>, W.grid_spmv, 256, 0, (const uint32_t *)L.slice_off.p,
+            MAG_LAUNCH_DEP(ctx, m.pdl, pcg_spmv_kernel<int16_t>, W.grid_spmv, 256, 0, (const uint32_t *)L.slice_off.p,
                        (const int16_t *)L.pcol.p, (const double *)L.val.p, (const double *)W.p_ext.p, W.q.p,
                        W.n, L.n_slices, L.row_lo, step, links_of(W, m), W.partials.p, W.scal.p, pq_target(W, m));
         else
-            MAG_LAUNCH(ctx, pcg_spmv_kernel<int32_t>, W.grid_spmv, 256, 0, (const uint32_t *)L.slice_off.p,
+            MAG_LAUNCH_DEP(ctx, m.pdl, pcg_spmv_kernel<int32_t>, W.grid_spmv, 256, 0, (const uint32_t *)L.slice_off.p,
                        (const int32_t *)L.col.p, (const double *)L.val.p, (const double *)W.p_ext.p, W.q.p,
                        W.n, L.n_slices, L.row_lo, step, links_of(W, m), W.partials.p, W.scal.p, pq_target(W, m));
     }
     reduce_scalars(ctx, ranks, m, kOffLocPq, kOffPq, 1);
     for (RankState &W : ranks)
-        MAG_LAUNCH(ctx, pcg_update_xr_kernel, W.grid_vec, 256, 0, W.x.p, W.r_ext, (const double *)W.p_ext.p,
+        MAG_LAUNCH_DEP(ctx, m.pdl, pcg_update_xr_kernel, W.grid_vec, 256, 0, W.x.p, W.r_ext, (const double *)W.p_ext.p,
                    (const double *)W.q.p, (const double *)W.dinv_ext, W.n, W.S->row_lo, step, W.S->push,
                    links_of(W, m), W.partials.p, W.scal.p, pair_target(W, m, parity ^ 1));
     reduce_scalars(ctx, ranks, m, kOffLocPair, kOffPair0 + 2 * (size_t)(parity ^ 1), 2);
     if (m.two_level) enqueue_coarse_solve(ctx, ranks, m, step);
     for (RankState &W : ranks)
-        MAG_LAUNCH(ctx, pcg_update_p_kernel, W.grid_ext, 256, 0, W.p_ext.p, (const double *)W.r_ext,
+        MAG_LAUNCH_DEP(ctx, m.pdl, pcg_update_p_kernel, W.grid_ext, 256, 0, W.p_ext.p, (const double *)W.r_ext,
                    (const double *)W.dinv_ext, W.S->ext_lo, W.S->ext_hi, step, W.halo, coarse_view(W, m),
                    links_of(W, m), W.scal.p);
 }
@@ -616,6 +616,7 @@ static bool small_cg_try(mag_ctx *ctx, RankState &W, const mag_options &opt, int
 static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const mag_options &opt) {
     SolveMode mode;
     mode.format = opt.spmv_format == 1 ? 1 : 2;
+    mode.pdl = !(ctx->tune & 512);
     if (ranks.size() > 1) mode.reduce = Reduce::kEmulated;
     else if (ranks[0].S->nranks > 1) mode.reduce = opt.allreduce == 1 ? Reduce::kNccl : Reduce::kMailbox;
     const bool compat = opt.compat != 0;
@@ -708,7 +709,7 @@ static SolveOutcome pcg_drive(mag_ctx *ctx, std::vector<RankState> &ranks, const
     MAG_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
     try {
         for (int i = 0; i < chunk; ++i) enqueue_iteration(ctx, ranks, i, mode);
-        for (RankState &W : ranks) MAG_LAUNCH(ctx, pcg_chunk_end_kernel, 1, 1, 0, chunk, W.scal.p);
+        for (RankState &W : ranks) MAG_LAUNCH_DEP(ctx, mode.pdl, pcg_chunk_end_kernel, 1, 1, 0, chunk, W.scal.p);
     } catch (...) {
         cudaStreamEndCapture(ctx->stream, &graph);
         if (graph) cudaGraphDestroy(graph);
