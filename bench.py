@@ -720,6 +720,10 @@ def run_ours(args):
         return
     its = max(int(last.iters), 1)
     iter_bytes = nbytes.value + 88 * n_local_rows
+    # device memory this process holds at the end of the run: the library's heap keeps its high-water mark reserved,
+    # so this is the peak of the step plus the bench's own result / proof buffers and the CUDA context
+    free_b, total_b = torch.cuda.mem_get_info(dev)
+    mem_gb = max_over_ranks((total_b - free_b) / 1e9)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
@@ -729,7 +733,7 @@ def run_ours(args):
                     "multi_gpu": None if world == 1 else "P2P halo stores fused into the CG update kernel, dot products "
                                  + ("allreduced by NCCL" if args.allreduce else "through peer-memory mailboxes inside the CG kernels"),
                     "triangles": E, "n_free": int(last.n_free), "nnz": int(last.nnz), "nnz_structural": int(last.nnz_structural),
-                    "n_coarse": int(last.n_coarse)},
+                    "n_coarse": int(last.n_coarse), "device_mem_gb_per_gpu_max": mem_gb},
         "proof": dict(proof, multi_gpu_vs_emulation=multi, failures=failures),
         "metrics": {"assembly_melem_s": E / (ms_asm * 1e-3) / 1e6, "assembly_ms": ms_asm,
                     "pcg_time_to_solve_s": ms_solve * 1e-3, "pcg_iters": int(last.iters),

@@ -92,6 +92,9 @@ extern "C" int mag_ctx_create(mag_ctx **out, int device) {
         c->sm_count = prop.multiProcessorCount;
         MAG_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
         c->stream = c->own_stream;
+        MAG_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+        MAG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        MAG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         MAG_CUDA(cudaMallocHost((void **)&c->h_scal, 128 * sizeof(double)));
         if (const char *t = std::getenv("MAG_TUNE")) c->tune = std::atoi(t);
         *out = c.release();
@@ -102,6 +105,7 @@ extern "C" void mag_ctx_destroy(mag_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->own_stream);
+    if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
     if (ctx->comm) {
         Comm *c = ctx->comm;
         // every rank unmaps its peers' slabs, then all ranks meet, and only then does anyone free the buffer it
@@ -124,6 +128,9 @@ extern "C" void mag_ctx_destroy(mag_ctx *ctx) {
     ctx->heap.destroy();
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
 }
 

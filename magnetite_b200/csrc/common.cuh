@@ -112,6 +112,10 @@ struct mag_ctx {
     bool rs_attr_set = false;           // radix sort (64-bit keys): dynamic shared memory opt-in done on this device
     bool rs32_attr_set = false;         // same, 32-bit keys
     mag::Comm *comm = nullptr;
+    // side stream for host<->device copies that run beside kernels of the run stream (aux_fork / aux_join below)
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool aux_busy = false;              // copies may still be in flight on aux_stream
     // pinned host scratch for scalar read-backs
     double *h_scal = nullptr;
 };
@@ -226,6 +230,22 @@ inline void copy_from_device(mag_ctx *ctx, T *dst, const T *src, size_t n, bool 
     MAG_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T),
                              dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                              ctx->stream));
+}
+
+// Work enqueued on ctx->aux_stream after this call starts once everything queued on the run stream so far is done.
+inline void aux_fork(mag_ctx *ctx) {
+    MAG_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    MAG_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    ctx->aux_busy = true;
+}
+// The run stream continues once everything queued on the aux stream so far is done.
+inline void aux_join(mag_ctx *ctx) {
+    MAG_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    MAG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+}
+// Before memory the aux stream may still touch is handed back (error paths: the join never happened).
+inline void aux_drain(mag_ctx *ctx) {
+    if (ctx && ctx->aux_busy) { cudaStreamSynchronize(ctx->aux_stream); ctx->aux_busy = false; }
 }
 
 struct EventTimer {       // CUDA-event phase timer on the run stream

@@ -790,18 +790,30 @@ struct PostBuffers {
     DevBuf<double> xfull, ux, uy, fx, fy, stress, sigma;
 };
 
-static void post_local(mag_ctx *ctx, mag_system *S, PostBuffers &B, bool want_sigma) {
+// side_out (one rank, host result arrays): ux, uy leave on the side stream while the reactions are computed, and
+// fx, fy while the stresses are; the caller joins the streams (aux_join) before it synchronises.
+static void post_local(mag_ctx *ctx, mag_system *S, PostBuffers &B, bool want_sigma, mag_result *side_out = nullptr) {
     const size_t N = S->n_nodes, E = S->n_elems;
     if (N) {
         MAG_LAUNCH(ctx, scatter_solution_kernel, cdiv(N, 256), 256, 0, (const uint8_t *)S->known.p,
                    (const uint32_t *)S->colmap.p, (const double *)S->bc_ux.p, (const double *)S->bc_uy.p,
                    (const double *)B.xfull.p, N, B.ux.p, B.uy.p);
+        if (side_out) {
+            aux_fork(ctx);
+            MAG_CUDA(cudaMemcpyAsync(side_out->ux, B.ux.p, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->aux_stream));
+            MAG_CUDA(cudaMemcpyAsync(side_out->uy, B.uy.p, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->aux_stream));
+        }
         const uint32_t n_owned_dof = 2 * (S->K.node_hi - S->K.node_lo);
         if (n_owned_dof)
             MAG_LAUNCH(ctx, reactions_kernel, cdiv(n_owned_dof, 256), 256, 0, (const uint32_t *)S->K.browptr.p,
                        (const uint32_t *)S->K.bcol.p, (const double *)S->K.bval.p, S->K.node_lo, n_owned_dof,
                        (const uint8_t *)S->known.p, (const double *)S->bc_fx.p, (const double *)S->bc_fy.p,
                        (const double *)B.ux.p, (const double *)B.uy.p, B.fx.p, B.fy.p);
+        if (side_out) {
+            aux_fork(ctx);
+            MAG_CUDA(cudaMemcpyAsync(side_out->fx, B.fx.p, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->aux_stream));
+            MAG_CUDA(cudaMemcpyAsync(side_out->fy, B.fy.p, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->aux_stream));
+        }
     }
     if (E) {
         upload_material(ctx, S->mat);
@@ -825,8 +837,9 @@ static void check_result_args(const mag_system *S, const mag_result *out) {
 }
 
 // scope 1 (multi-rank): only this rank's slice of every array — nodes by mag_partition_nodes, elements split evenly.
+// nodal false: ux, uy, fx, fy have already left on the side stream (post_local).
 static void download_result(mag_ctx *ctx, const mag_system *S, PostBuffers &B, mag_result *out, bool want_sigma,
-                            int scope = 0) {
+                            int scope = 0, bool nodal = true) {
     const size_t N = S->n_nodes, E = S->n_elems;
     const bool odev = out->on_device != 0;
     size_t n0 = 0, n1 = N, e0 = 0, e1 = E;
@@ -837,10 +850,12 @@ static void download_result(mag_ctx *ctx, const mag_system *S, PostBuffers &B, m
         partition_nodes(E, S->nranks, S->rank, &lo, &hi);
         e0 = lo; e1 = hi;
     }
-    copy_from_device(ctx, out->ux + n0, (const double *)B.ux.p + n0, n1 - n0, odev);
-    copy_from_device(ctx, out->uy + n0, (const double *)B.uy.p + n0, n1 - n0, odev);
-    copy_from_device(ctx, out->fx + n0, (const double *)B.fx.p + n0, n1 - n0, odev);
-    copy_from_device(ctx, out->fy + n0, (const double *)B.fy.p + n0, n1 - n0, odev);
+    if (nodal) {
+        copy_from_device(ctx, out->ux + n0, (const double *)B.ux.p + n0, n1 - n0, odev);
+        copy_from_device(ctx, out->uy + n0, (const double *)B.uy.p + n0, n1 - n0, odev);
+        copy_from_device(ctx, out->fx + n0, (const double *)B.fx.p + n0, n1 - n0, odev);
+        copy_from_device(ctx, out->fy + n0, (const double *)B.fy.p + n0, n1 - n0, odev);
+    }
     copy_from_device(ctx, out->stress + e0, (const double *)B.stress.p + e0, e1 - e0, odev);
     if (want_sigma) copy_from_device(ctx, out->sigma + 3 * e0, (const double *)B.sigma.p + 3 * e0, (e1 - e0) * 3, odev);
 }
@@ -879,6 +894,7 @@ static void solve_impl(mag_system *S, const mag_options *opt_in, mag_result *out
     phase.start();
     const bool want_sigma = out->sigma != nullptr;
     PostBuffers B;
+    struct AuxGuard { mag_ctx *c; ~AuxGuard() { aux_drain(c); } } aux_guard{ctx};   // error paths: before B is handed back
     B.xfull.alloc(ctx, ext_len(S));
     B.ux.alloc(ctx, N); B.uy.alloc(ctx, N); B.fx.alloc(ctx, N); B.fy.alloc(ctx, N);
     B.stress.alloc(ctx, E);
@@ -887,7 +903,9 @@ static void solve_impl(mag_system *S, const mag_options *opt_in, mag_result *out
         MAG_CUDA(cudaMemcpyAsync(B.xfull.p + S->row_lo, ranks[0].x.p, (size_t)ranks[0].n * sizeof(double),
                                  cudaMemcpyDeviceToDevice, ctx->stream));
     allgather_slices(ctx, B.xfull.p, S->all_row_lo);
-    post_local(ctx, S, B, want_sigma);
+    // one rank, host result arrays: the nodal fields cross PCIe beside the remaining post-processing kernels
+    const bool side = S->nranks == 1 && !out->on_device && N >= (1u << 16) && !(ctx->tune & 2048);
+    post_local(ctx, S, B, want_sigma, side ? out : nullptr);
     if (S->nranks > 1) {          // every rank returns complete fx, fy
         allgather_slices(ctx, B.fx.p, S->all_node_lo);
         allgather_slices(ctx, B.fy.p, S->all_node_lo);
@@ -895,8 +913,10 @@ static void solve_impl(mag_system *S, const mag_options *opt_in, mag_result *out
     st.ms_post = phase.stop();
 
     phase.start();
-    download_result(ctx, S, B, out, want_sigma, opt.result_scope);
+    download_result(ctx, S, B, out, want_sigma, opt.result_scope, !side);
+    if (side) aux_join(ctx);
     MAG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (side) ctx->aux_busy = false;
     st.ms_download = phase.stop();
     st.kernel_launches = ctx->launches - launches_before;
     S->stats.iters = st.iters;

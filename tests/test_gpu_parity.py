@@ -279,6 +279,27 @@ def test_full_size_properties_1m_triangles(ctx):
     assert 0.5 < mid / (69e9 * 3.0 / 2000.0) < 1.5            # ~ E * strain in the middle of the plate
 
 
+def test_two_level_solve_is_bit_identical_run_to_run_on_a_large_grid(ctx):
+    """2.1 M unknowns: the p-update runs on more CTAs than are resident at once, so a CTA scheduled late would see
+    any scalar the same launch rewrites (the round-1 race on r.z).  Two solves of one system and a
+    solve of a second system built from the same mesh must agree in every bit and in the iteration count."""
+    mesh = meshgen.plate(1500, 700)
+    opt = _lib.default_options(precond=2)
+    outs = []
+    with solver.System(mesh, META, ctx) as S:
+        assert S.n_free > 2_000_000
+        outs.append(S.solve(opt)); outs.append(S.solve(opt))
+        rr, bb = S.true_residual(outs[0].ux, outs[0].uy)
+        assert rr <= (2e-9) ** 2 * bb
+    with solver.System(mesh, META, ctx) as S:
+        outs.append(S.solve(opt))
+    assert outs[0].stats["precond_used"] == 2 and outs[0].stats["converged"] == 1
+    for o in outs[1:]:
+        assert o.stats["iters"] == outs[0].stats["iters"]
+        for k in ("ux", "uy", "fx", "fy", "stress"):
+            assert getattr(o, k).tobytes() == getattr(outs[0], k).tobytes(), k
+
+
 def test_config3_kff_bit_exact_against_oracle(ctx):
     """BASELINE configs[2] (1 M triangles, 1000 x 500 cells) at full size: K_ff (pattern and values), rhs and the
     free-DOF numbering bit for bit against the oracle's assembly + partition (solver.rs:290-404, 126-137) — a few
@@ -505,6 +526,35 @@ def test_single_cluster_solve_matches_the_general_path(ctx):
         assert again[0].ux.tobytes() == again[1].ux.tobytes()                               # bit-identical run to run
     finally:
         general.close()
+
+
+def test_programmatic_and_plain_launches_of_the_loop_agree(ctx):
+    """The kernels of the CG loop are launched as programmatic dependents inside the graph (common.cuh:
+    MAG_LAUNCH_DEP, every kernel starts with griddepcontrol.wait); MAG_TUNE=512 launches them plainly.  Host arrays
+    of 65 536 nodes and more move their prescribed values in and their nodal results out on a side stream beside
+    the kernels (system.cuh, solve.cuh: aux_fork / aux_join); MAG_TUNE=2048 keeps everything on the run stream.
+    Ordering is the only thing either switch changes, so every bit of the result must be the same — Jacobi and
+    two-level, one GPU and three virtual ranks."""
+    import os
+    os.environ["MAG_TUNE"] = str(512 + 2048)
+    try:
+        plain = _lib.Context(0)
+    finally:
+        del os.environ["MAG_TUNE"]
+    try:
+        mesh = meshgen.jitter(meshgen.plate(400, 180))
+        assert mesh.n_nodes >= 65536
+        for opt in (dict(precond=1), dict(precond=2, coarse_aggregates=64)):
+            a = solver.solve_soa(mesh, META, ctx, _lib.default_options(**opt))
+            b = solver.solve_soa(mesh, META, plain, _lib.default_options(**opt))
+            va = solver.virtual_rank_solve(mesh, META, 3, ctx, _lib.default_options(**opt))
+            vb = solver.virtual_rank_solve(mesh, META, 3, plain, _lib.default_options(**opt))
+            for x, y in ((a, b), (va, vb)):
+                assert x.stats["iters"] == y.stats["iters"] and x.stats["converged"] == 1
+                for k in ("ux", "uy", "fx", "fy", "stress"):
+                    assert getattr(x, k).tobytes() == getattr(y, k).tobytes(), (opt, k)
+    finally:
+        plain.close()
 
 
 def test_narrow_and_wide_sell_index_streams_agree(ctx):
