@@ -712,6 +712,12 @@ def run_ours(args):
     if not args.no_cpu_baseline and world == 1:
         _, _, cpu = cpu_baseline_block(args, world, 3, 1)
 
+    # device memory this process holds at the end of the run: the library's heap keeps its high-water mark reserved,
+    # so this is the peak of the step plus the bench's own result / proof buffers and the CUDA context.
+    # (max_over_ranks is a collective: every rank calls it, BEFORE the ranks part ways below.)
+    free_b, total_b = torch.cuda.mem_get_info(dev)
+    mem_gb = max_over_ranks((total_b - free_b) / 1e9)
+
     if rank != 0:
         barrier()
         lib.mag_devmesh_free(dm)
@@ -720,10 +726,6 @@ def run_ours(args):
         return
     its = max(int(last.iters), 1)
     iter_bytes = nbytes.value + 88 * n_local_rows
-    # device memory this process holds at the end of the run: the library's heap keeps its high-water mark reserved,
-    # so this is the peak of the step plus the bench's own result / proof buffers and the CUDA context
-    free_b, total_b = torch.cuda.mem_get_info(dev)
-    mem_gb = max_over_ranks((total_b - free_b) / 1e9)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,

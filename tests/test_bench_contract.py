@@ -64,3 +64,16 @@ def test_gpu_arm_has_no_cpu_fallback(built):
                        timeout=300, env=_env(), cwd=ROOT)
     assert r.returncode != 0
     assert not any(ln.lstrip().startswith("{") for ln in r.stdout.splitlines())              # no benchmark line was produced
+
+
+def test_no_collective_after_the_ranks_part_ways():
+    """bench.py's ranks != 0 leave (barrier, free, close) while rank 0 builds and prints the line: a collective
+    helper called by rank 0 alone in that stretch pairs with the other ranks' final barrier and the job hangs at
+    exit (it happened once, with a device-memory figure added to the line).  Static check of the source."""
+    src = (Path(__file__).resolve().parent.parent / "bench.py").read_text()
+    start = src.index("    if rank != 0:\n        barrier()")
+    end = src.index("print(json.dumps(line)", start)
+    stretch = src[start:end]
+    after_return = stretch[stretch.index("return") :]
+    for helper in ("max_over_ranks(", "sum_over_ranks(", "barrier()", "all_reduce(", "all_gather("):
+        assert helper not in after_return, helper
