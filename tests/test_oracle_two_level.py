@@ -1,0 +1,92 @@
+"""CPU: the numpy / scipy restatement of the default solver (oracle/two_level.py: Jacobi-PCG and the two-level
+preconditioner, written from their definitions) needs EXACTLY the iteration counts the B200 needed — the counts are
+read from the bench lines committed under profiles/, so this ties the measured GPU runs to an independent statement of
+the same mathematics without a GPU.  It also checks the restatement itself: same solution as the oracle's plain CG,
+far fewer iterations than Jacobi, Jacobi fallback condition on a negative definite system."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from magnetite_b200 import meshgen
+from oracle import oracle as O
+from oracle import two_level as T
+
+META = meshgen.EXAMPLE_MATERIAL
+PROFILES = Path(__file__).resolve().parent.parent / "profiles"
+
+
+def bench_line(name):
+    return json.loads((PROFILES / name).read_text().strip().splitlines()[-1])
+
+
+def test_counts_of_the_400x200_plate_match_the_b200():
+    """bench.py's same-config sample: mag_solve on the 400 x 200 plate, Jacobi-PCG and the default (auto: two-level)."""
+    gpu = bench_line("r2_bench_c4_1gpu.json")["metrics"]["same_config_sample"]
+    assert "400x200" in gpu["workload"]
+    S = T.reduced_system(meshgen.plate(400, 200), META)
+    assert T.default_kind(S.A.shape[0]) == 2
+    assert T.coarse_grid(S.A.shape[0], S.box)[:2] == (9, 4)
+    x2, it2 = T.pcg(S, 2)
+    x1, it1 = T.pcg(S, 1)
+    assert it2 == gpu["default"]["pcg_iters"] == 450
+    assert it1 == gpu["jacobi"]["pcg_iters"] == 2801
+    assert np.linalg.norm(x2 - x1) / np.linalg.norm(x1) < 1e-6            # both within kappa * 1e-9 of the solution
+    for x in (x1, x2):
+        assert np.linalg.norm(S.rhs - S.A @ x) <= 2e-9 * np.linalg.norm(S.rhs)
+
+
+def test_count_of_the_1m_triangle_plate_matches_the_b200():
+    """BASELINE config 3 through the default options (metrics.baseline_configs of the committed 1-GPU line)."""
+    gpu = bench_line("r2_bench_c4_1gpu.json")["metrics"]["baseline_configs"]["config3_plate_1m"]
+    assert gpu["precond_used"] == 2
+    S = T.reduced_system(meshgen.plate(1000, 500), META)
+    assert T.coarse_grid(S.A.shape[0], S.box)[:2] == (22, 11)
+    x, it = T.pcg(S, 2)
+    assert it == gpu["pcg_iters"] == 424
+    assert np.linalg.norm(S.rhs - S.A @ x) <= 2e-9 * np.linalg.norm(S.rhs)
+
+
+def test_count_of_the_multi_gpu_proof_plate_matches_the_b200():
+    """The plate bench.py solves to 1e-12 on 8 real GPUs and on 8 emulated ranks (proof.multi_gpu_vs_emulation):
+    partial sums are added rank by rank there, so the count may move by rounding (two iterations allowed)."""
+    cases = bench_line("r2_bench_c4_8gpu.json")["proof"]["multi_gpu_vs_emulation"]
+    assert "768x384" in cases["workload"]
+    two = [c for c in cases["cases"] if c["precond"] == 2][0]
+    assert two["iters_real"] == two["iters_emulated"]
+    S = T.reduced_system(meshgen.plate(768, 384), META)
+    _, it = T.pcg(S, 2, rel_tol=1e-12)
+    assert abs(it - two["iters_real"]) <= 2
+
+
+def test_restatement_against_the_oracle_and_its_own_definition():
+    mesh = meshgen.jitter(meshgen.plate(60, 30))
+    S = T.reduced_system(mesh, META)
+    ref = O.run(O.Mesh(mesh), META, O.cg_options(), dense=False)              # the reference's plain CG, cost <= 1e-4
+    u = np.stack([ref["ux"], ref["uy"]], 1).ravel()[2 * S.node + S.axis]
+    P = T.prolongation(S, 32)
+    assert P.shape[1] == 3 * 32 and (np.diff(P.tocsr().indptr) == 2).all()    # one translation + the rotation per row
+    assert np.array_equal(P.data.astype(np.float32).astype(np.float64), P.data)
+    x2, it2 = T.pcg(S, 2, rel_tol=1e-12, coarse_aggregates=32)
+    x1, it1 = T.pcg(S, 1, rel_tol=1e-12)
+    x0, it0 = T.pcg(S, 0, rel_tol=1e-12)
+    assert it2 < 0.6 * it1 and it1 <= it0
+    for x in (x0, x1, x2):
+        assert np.linalg.norm(x - u) / np.linalg.norm(u) < 1e-8
+    # M^-1 is symmetric positive definite: CG's requirement (checked on random vectors)
+    M, info = T.preconditioner(S, 2, 32)
+    rng = np.random.default_rng(3)
+    a, b = rng.normal(size=S.A.shape[0]), rng.normal(size=S.A.shape[0])
+    assert info["n_coarse"] == 96
+    assert abs(a @ M(b) - b @ M(a)) <= 1e-10 * abs(a @ M(b)) + 1e-20 and a @ M(a) > 0
+
+
+def test_negative_definite_system_has_no_coarse_factor():
+    """All-clockwise mesh: K_ff is negative definite, Ac with it — the device then falls back to Jacobi
+    (tests/test_gpu_parity.py::test_two_level_on_examples_and_indefinite_meshes)."""
+    m = meshgen.plate(40, 20)
+    cw = m.__class__(m.x, m.y, m.n0, m.n2, m.n1, m.ux, m.uy, m.fx, m.fy, m.known)
+    S = T.reduced_system(cw, META)
+    with pytest.raises(ValueError):
+        T.preconditioner(S, 2, 16)
