@@ -1,5 +1,5 @@
 """CPU: the numpy / scipy restatement of the default solver (oracle/two_level.py: Jacobi-PCG and the two-level
-preconditioner, written from their definitions) needs EXACTLY the iteration counts the B200 needed — the counts are
+preconditioner, written from their definitions) needs the iteration counts the B200 needed (to the iteration when this was written; two of slack asserted) — the counts are
 read from the bench lines committed under profiles/, so this ties the measured GPU runs to an independent statement of
 the same mathematics without a GPU.  It also checks the restatement itself: same solution as the oracle's plain CG,
 far fewer iterations than Jacobi, Jacobi fallback condition on a negative definite system."""
@@ -15,6 +15,10 @@ from oracle import two_level as T
 
 META = meshgen.EXAMPLE_MATERIAL
 PROFILES = Path(__file__).resolve().parent.parent / "profiles"
+# The counts below were EQUAL on both sides when this was written (8 host cores).  The order in which a BLAS adds a
+# dot product depends on its thread count, and a stop test can fall either side of an iteration boundary on rounding
+# alone, so the assertions leave two iterations of slack.
+SLACK = 2
 
 
 def bench_line(name):
@@ -30,8 +34,8 @@ def test_counts_of_the_400x200_plate_match_the_b200():
     assert T.coarse_grid(S.A.shape[0], S.box)[:2] == (9, 4)
     x2, it2 = T.pcg(S, 2)
     x1, it1 = T.pcg(S, 1)
-    assert it2 == gpu["default"]["pcg_iters"] == 450
-    assert it1 == gpu["jacobi"]["pcg_iters"] == 2801
+    assert gpu["default"]["pcg_iters"] == 450 and gpu["jacobi"]["pcg_iters"] == 2801
+    assert abs(it2 - 450) <= SLACK and abs(it1 - 2801) <= SLACK, (it2, it1)
     assert np.linalg.norm(x2 - x1) / np.linalg.norm(x1) < 1e-6            # both within kappa * 1e-9 of the solution
     for x in (x1, x2):
         assert np.linalg.norm(S.rhs - S.A @ x) <= 2e-9 * np.linalg.norm(S.rhs)
@@ -44,7 +48,7 @@ def test_count_of_the_1m_triangle_plate_matches_the_b200():
     S = T.reduced_system(meshgen.plate(1000, 500), META)
     assert T.coarse_grid(S.A.shape[0], S.box)[:2] == (22, 11)
     x, it = T.pcg(S, 2)
-    assert it == gpu["pcg_iters"] == 424
+    assert gpu["pcg_iters"] == 424 and abs(it - 424) <= SLACK, it
     assert np.linalg.norm(S.rhs - S.A @ x) <= 2e-9 * np.linalg.norm(S.rhs)
 
 
@@ -57,7 +61,7 @@ def test_count_of_the_multi_gpu_proof_plate_matches_the_b200():
     assert two["iters_real"] == two["iters_emulated"]
     S = T.reduced_system(meshgen.plate(768, 384), META)
     _, it = T.pcg(S, 2, rel_tol=1e-12)
-    assert abs(it - two["iters_real"]) <= 2
+    assert abs(it - two["iters_real"]) <= SLACK, it
 
 
 def test_restatement_against_the_oracle_and_its_own_definition():
