@@ -661,6 +661,50 @@ def run_ours(args):
                                            "rel_residual": float(sol.stats["final_residual"] / sol.stats["b_norm"])}
         except Exception as err:
             example["config3_plate_1m"] = {"error": str(err)}
+        # configs[4]: the perforated plate at its per-GPU size (the weak-scaling unit: 16 M DOF before the holes),
+        # device-generated like the timed workload, library defaults.  The whole 8-GPU job: `--workload c5 --gpus 8`.
+        if not weak:
+            dm5 = C.c_void_p()
+            try:
+                _lib.check(lib.mag_devmesh_perforated(ctx.handle, args.nx, args.ny, 2.0, 64, 16, 3.0, C.byref(dm5)),
+                           "mag_devmesh_perforated")
+                view5 = _lib.MagMesh()
+                _lib.check(lib.mag_devmesh_view(dm5, C.byref(view5)), "mag_devmesh_view")
+                n5, e5 = int(view5.n_nodes), int(view5.n_elems)
+                out5, res5 = device_result(n5, e5)
+                ms5, st5 = [], None
+                for _ in range(3):
+                    st5 = _lib.MagStats()
+                    ev0.record(stream)
+                    _lib.check(lib.mag_solve(ctx.handle, C.byref(view5), C.byref(mat), C.byref(opt), C.byref(res5),
+                                             C.byref(st5)), "mag_solve(config 5 unit)")
+                    ev1.record(stream)
+                    torch.cuda.synchronize()
+                    ms5.append(ev0.elapsed_time(ev1))
+                sys5, sa5 = C.c_void_p(), _lib.MagStats()
+                _lib.check(lib.mag_assemble(ctx.handle, C.byref(view5), C.byref(mat), C.byref(opt), C.byref(sys5), C.byref(sa5)),
+                           "mag_assemble(config 5 unit)")
+                rr5, bb5 = C.c_double(), C.c_double()
+                rc5 = lib.mag_system_residual(sys5, out5["ux"].data_ptr(), out5["uy"].data_ptr(), 1, C.byref(rr5), C.byref(bb5))
+                lib.mag_system_free(sys5)
+                _lib.check(rc5, "mag_system_residual(config 5 unit)")
+                true5 = (rr5.value / bb5.value) ** 0.5 if bb5.value > 0 else 0.0
+                step5 = statistics.mean(ms5[1:])
+                example["config5_perforated_unit"] = {
+                    "workload": "perforated (holes of radius 16h at pitch 64h) " + workload_name(args.nx, args.ny)
+                                + f" before the holes; {e5} triangles, {int(st5.n_free)} free DOF: the per-GPU unit of the weak-scaling job",
+                    "ms_per_step": step5, "melem_s": e5 / (step5 * 1e-3) / 1e6, "pcg_iters": int(st5.iters),
+                    "precond_used": int(st5.precond_used), "pcg_time_to_solve_s": st5.ms_solve * 1e-3,
+                    "assembly_ms": st5.ms_elem + st5.ms_sort + st5.ms_reduce + st5.ms_bc,
+                    "true_rel_residual": true5}
+                if not (true5 <= MAX_TRUE_REL_RESIDUAL):
+                    failures.append(f"config 5 unit: true relative residual {true5:.3e} > {MAX_TRUE_REL_RESIDUAL}")
+                del out5
+            except Exception as err:
+                example["config5_perforated_unit"] = {"error": str(err)}
+            finally:
+                if dm5:
+                    lib.mag_devmesh_free(dm5)
 
     # ---- end to end: pinned host buffers through mag_solve ----------------------------------
     e2e = None
