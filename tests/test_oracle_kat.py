@@ -218,3 +218,35 @@ def test_all_cores_pcg_agrees_with_the_sequential_port():
     assert it0 == 0 and not x0.any()
     xe, ite, _ = MT.pcg((np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(0)), np.zeros(0), threads=4)
     assert xe.size == 0 and ite == 0
+
+
+def test_oracle_matches_the_formulas_of_the_reference_documentation():
+    """The reference ships no numeric vectors, but its own documentation states the element formulas independently
+    of the code (under-the-hood.md:294-299 and :577-582 D; :520-524 B with the 1/(2A) factor, x_ij = x_i - x_j and
+    y_ij = y_i - y_j over nodes 1..3, :592; :551 and :572 k_e = B^T D B t A; :598-604 the area as half a determinant —
+    printed there with a third column of zeros, which would vanish: the ones column of solver.rs:187-193 is meant;
+    :621-640 the scatter of k_e into K by node pairs, DOF = 2*node + axis).  The oracle follows the CODE's operation
+    order, so agreement with these closed forms is to rounding, not bitwise: 1e-13 relative to the largest entry."""
+    rng = np.random.default_rng(7)
+    pts = rng.uniform(-5.0, 5.0, size=(40, 2))
+    conn = np.array([rng.choice(40, 3, replace=False) for _ in range(60)], np.uint32)
+    m = tri_mesh(pts, conn)
+    om = O.Mesh(m)
+    area = O.element_area(om)
+    ke = O.element_stiffness(om, META)
+    D_doc = E / (1.0 - NU ** 2) * np.array([[1.0, NU, 0.0], [NU, 1.0, 0.0], [0.0, 0.0, (1.0 - NU) / 2.0]])
+    np.testing.assert_allclose(O.stress_strain(NU, E), D_doc, rtol=1e-15)
+    K_doc = np.zeros((80, 80))
+    for e, (a, b, c) in enumerate(conn.astype(int)):
+        (x1, y1), (x2, y2), (x3, y3) = pts[a], pts[b], pts[c]
+        A_doc = 0.5 * np.linalg.det(np.array([[x1, y1, 1.0], [x2, y2, 1.0], [x3, y3, 1.0]]))
+        assert area[e] == pytest.approx(A_doc, rel=1e-12)
+        y23, y31, y12, x32, x13, x21 = y2 - y3, y3 - y1, y1 - y2, x3 - x2, x1 - x3, x2 - x1
+        B_doc = np.array([[y23, 0, y31, 0, y12, 0], [0, x32, 0, x13, 0, x21], [x32, y23, x13, y31, x21, y12]]) / (2.0 * A_doc)
+        ke_doc = B_doc.T @ D_doc @ B_doc * T * A_doc
+        assert np.abs(ke[e] - ke_doc).max() <= 1e-13 * np.abs(ke_doc).max()
+        for lr, nr in enumerate((a, b, c)):
+            for lc, nc in enumerate((a, b, c)):
+                K_doc[2 * nr:2 * nr + 2, 2 * nc:2 * nc + 2] += ke_doc[2 * lr:2 * lr + 2, 2 * lc:2 * lc + 2]
+    K = O.assemble_dense(om, ke)
+    assert np.abs(K - K_doc).max() <= 1e-12 * np.abs(K_doc).max()
