@@ -15,8 +15,13 @@
  * reference *source* line by line (citations below are file:line under the
  * reference checkout) and restates the published algorithms of those crates
  * at the reference's call sites.  It is pinned only against analytic
- * known-answer tests (patch test, rigid-body modes) and an independent
- * numpy/scipy restatement (oracle/reference_semantics.py).
+ * known-answer tests (patch test, rigid-body modes), the closed forms of the
+ * reference's own documentation (under-the-hood.md), an independent
+ * numpy/scipy restatement (oracle/reference_semantics.py) and — to the
+ * resolution of a picture, about 1 % of the displacement, nowhere near
+ * rounding level — the one output of its own solver the reference publishes:
+ * the true-scale deformed outline of examples/linkedin-logo/output.png
+ * (tests/test_reference_picture.py, tests/golden/measure_reference_picture.py).
  *
  * All arithmetic is fp64, compiled with -ffp-contract=off so that every
  * multiply and add is rounded separately, as rustc does.

@@ -1,0 +1,105 @@
+"""The one numeric output of its own solver the reference publishes: the TRUE-SCALE deformed shape of its
+linkedin-logo example (examples/linkedin-logo/output.png, drawn by scripts/plot.py:143-147 at (x + ux, y + uy)).
+
+tests/golden/measure_reference_picture.py read that picture in the build container and committed what it shows —
+the intervals the solved and the initial model cover along horizontal and vertical lines every 25 units, one pixel
+= 0.73 units — as tests/golden/reference_linkedin_picture.json.  Here the same example (same outline, same
+input.json, the stand-in mesher's triangulation instead of gmsh's: tests/golden/example_linkedin.npz) is solved by
+the oracle (CPU) and by the library (GPU) and the deformed outline is laid over the reference's.
+
+What this pins, to ~1 % of the 150-unit displacement: the boundary-rule semantics (which nodes are held, which are
+pulled), plane STRESS (plane strain would contract the waist by 0.49 instead of 0.33 of the stretch), the assembly
+and the solve, signs and axes, and that nothing is magnified.  It cannot pin rounding-level arithmetic — the oracle
+header's "parity unpinned" stays true for that — but it is an output of the reference itself.
+"""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from magnetite_b200 import meshgen
+from magnetite_b200.datatypes import MeshSoA
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+PICTURE = json.loads((GOLDEN / "reference_linkedin_picture.json").read_text())
+UNITS_PER_PIXEL = 1.0 / PICTURE["panels"]["solved"]["pixels_per_unit"]
+# an edge in the picture: half a pixel of anti-aliasing counted as model + half a pixel of sampling + the two
+# triangulations' different boundary vertices on curved edges
+TOL = 2.0 * UNITS_PER_PIXEL + 0.4
+
+
+def example():
+    g = np.load(GOLDEN / "example_linkedin.npz")
+    mesh = MeshSoA(g["x"], g["y"], g["n0"], g["n1"], g["n2"], g["bc_ux"], g["bc_uy"], g["bc_fx"], g["bc_fy"], g["known"])
+    meta = meshgen.EXAMPLE_MATERIAL.__class__(*g["material"])
+    return g, mesh, meta
+
+
+def outline_edges(tri):
+    """Edges that belong to exactly one triangle: the outline (outer boundary and holes)."""
+    e = np.concatenate([tri[:, [0, 1]], tri[:, [1, 2]], tri[:, [2, 0]]])
+    e.sort(axis=1)
+    uniq, count = np.unique(e, axis=0, return_counts=True)
+    return uniq[count == 1]
+
+
+def picture_points(panel):
+    """Every point where a line of the picture enters or leaves the model: (x, y) on the reference's outline."""
+    pts = []
+    for line in PICTURE["panels"][panel]["along_y"].values():
+        pts += [(v, line["at"]) for iv in line["intervals"] for v in iv]
+    for line in PICTURE["panels"][panel]["along_x"].values():
+        pts += [(line["at"], v) for iv in line["intervals"] for v in iv]
+    return np.array(pts)
+
+
+def distance_to_outline(points, px, py, edges):
+    """Distance of every point to the nearest outline segment."""
+    a = np.stack([px[edges[:, 0]], py[edges[:, 0]]], 1)[None]        # (1, S, 2)
+    b = np.stack([px[edges[:, 1]], py[edges[:, 1]]], 1)[None]
+    p = points[:, None, :]                                            # (P, 1, 2)
+    ab = b - a
+    t = np.clip(((p - a) * ab).sum(2) / np.maximum((ab * ab).sum(2), 1e-300), 0.0, 1.0)
+    return np.linalg.norm(p - (a + t[..., None] * ab), axis=2).min(1)
+
+
+def misfit(panel, px, py, tri):
+    """(number of picture points, their largest and mean distance to our outline)."""
+    d = distance_to_outline(picture_points(panel), px, py, outline_edges(tri))
+    return len(d), float(d.max()), float(d.mean())
+
+
+def check(ux, uy, g):
+    tri = np.stack([g["n0"], g["n1"], g["n2"]], 1).astype(np.int64)
+    x, y = g["x"], g["y"]
+    # the geometry first: the undeformed outline is the picture's "Initial Model"
+    n0, worst0, mean0 = misfit("initial", x, y, tri)
+    assert n0 >= 200 and worst0 <= TOL and mean0 <= 0.5 * TOL, (n0, worst0, mean0)
+    # the solution: every point of the reference's deformed outline lies on ours, as closely as the undeformed one
+    # (measured: 254 points, worst 1.46 / mean 0.58 units against 1.35 / 0.57 for the geometry alone)
+    n, worst, mean = misfit("solved", x + ux, y + uy, tri)
+    assert n >= 240 and worst <= TOL and mean <= mean0 + 0.1, (n, worst, mean)
+    # and the comparison has teeth: no lateral contraction, plane strain's contraction (0.49 / 0.33 of it), a
+    # 2 % error of the stretch or a magnified plot do not fit
+    for fx, fy in ((0.0, 1.0), (0.49 / 0.33, 1.0), (1.1, 1.0), (1.0, 0.98), (1.02, 1.02)):
+        assert misfit("solved", x + fx * ux, y + fy * uy, tri)[1] > 1.25 * TOL, (fx, fy)
+
+
+def test_oracle_solution_lies_on_the_reference_picture():
+    from oracle import oracle as O
+    g, mesh, meta = example()
+    res = O.run(O.Mesh(mesh), meta, O.cg_options(), dense=False)       # the reference's solver semantics
+    check(res["ux"], res["uy"], g)
+    # ... and the committed fixture is that solution
+    assert np.linalg.norm(res["ux"] - g["ux"]) <= 1e-9 * np.linalg.norm(g["ux"])
+
+
+@pytest.mark.gpu
+def test_gpu_solution_lies_on_the_reference_picture(ctx):
+    from magnetite_b200 import _lib, solver
+    g, mesh, meta = example()
+    sol = solver.solve_soa(mesh, meta, ctx, _lib.default_options(compat=1))
+    check(sol.ux, sol.uy, g)
+    sol = solver.solve_soa(mesh, meta, ctx, _lib.default_options())   # the library's default solver, same picture
+    check(sol.ux, sol.uy, g)
