@@ -7,7 +7,8 @@ Nothing of the picture is copied: this script reads it where it lies, finds the 
 by eye, say the first vertical line is x = 0 and the first horizontal line from the top is y = 100), and writes the
 x-intervals the model covers along horizontal lines and the y-intervals along vertical lines, every 25 units, for
 both panels, into tests/golden/reference_linkedin_picture.json — a few hundred numbers with a resolution of one
-pixel = 0.73 units.  tests/test_reference_picture.py compares the oracle's (CPU) and the library's (GPU) solution of
+pixel = 0.73 units — and, for the solved panel, the stress colour on a 12.5-unit grid (red minus blue of the "coolwarm"
+face colour, a monotone function of the plotted stress).  tests/test_reference_picture.py compares the oracle's (CPU) and the library's (GPU) solution of
 the same example with them.
 
     python tests/golden/measure_reference_picture.py        # needs /root/reference and Pillow
@@ -98,9 +99,26 @@ def main():
                 if iv:
                     panel["along_x"][str(X)] = {"at": round(float(x_of(c + 0.5)), 3),
                                                 "intervals": [[b, a] for a, b in iv][::-1]}      # ascending y
+        if name == "solved":
+            # the stress colours (scripts/plot.py:136-141,154-158: cmap "coolwarm" over [min stress, max stress], faces
+            # drawn with alpha 0.7): on a 12.5-unit grid, where the 7x7 pixel patch around the point is all model, the
+            # median colour of its brighter half (the darker half is the black mesh lines), un-blended from the
+            # background, as red minus blue — a monotone function of the colormap parameter, hence of the stress
+            colour = []
+            for Y in np.arange(-637.5, 160.0, 12.5):
+                for X in np.arange(0.0, 640.0, 12.5):
+                    r, c = row_of(Y), col_of(X)
+                    if not (r0 + 4 <= r <= r1 - 4 and c0 + 4 <= c <= c1 - 4) or not model[r - 3:r + 4, c - 3:c + 4].all():
+                        continue
+                    patch = im[r - 3:r + 4, c - 3:c + 4].reshape(-1, 3).astype(float)
+                    lum = patch.sum(1)
+                    rgb = (np.median(patch[lum >= np.percentile(lum, 50)], axis=0) - 0.3 * BACKGROUND) / 0.7
+                    colour.append([round(float(x_of(c + 0.5)), 2), round(float(y_of(r + 0.5)), 2), round(float(rgb[0] - rgb[2]), 1)])
+            panel["red_minus_blue"] = colour
         result["panels"][name] = panel
-    OUT.write_text(json.dumps(result, indent=1) + "\n")
+    OUT.write_text(json.dumps(result, separators=(",", ":")) + "\n")
     s, i = result["panels"]["solved"], result["panels"]["initial"]
+    print(f"{len(s['red_minus_blue'])} colour samples")
     print(f"{OUT.name}: {len(s['along_y'])} + {len(s['along_x'])} lines of the solved model, "
           f"{len(i['along_y'])} + {len(i['along_x'])} of the initial one, {s['pixels_per_unit']} px per unit")
 

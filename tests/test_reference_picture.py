@@ -9,7 +9,8 @@ the oracle (CPU) and by the library (GPU) and the deformed outline is laid over 
 
 What this pins, to ~1 % of the 150-unit displacement: the boundary-rule semantics (which nodes are held, which are
 pulled), plane STRESS (plane strain would contract the waist by 0.49 instead of 0.33 of the stretch), the assembly
-and the solve, signs and axes, and that nothing is magnified.  It cannot pin rounding-level arithmetic — the oracle
+and the solve, signs and axes, and that nothing is magnified; the colours pin the ORDER of the element stresses and
+the sign rule of solver.rs:524-530.  It cannot pin rounding-level arithmetic — the oracle
 header's "parity unpinned" stays true for that — but it is an output of the reference itself.
 """
 import json
@@ -86,11 +87,45 @@ def check(ux, uy, g):
         assert misfit("solved", x + fx * ux, y + fy * uy, tri)[1] > 1.25 * TOL, (fx, fy)
 
 
+def elements_at(points, px, py, tri):
+    """Index of the triangle that holds each point (-1: none)."""
+    ax, ay, bx, by, cx, cy = px[tri[:, 0]], py[tri[:, 0]], px[tri[:, 1]], py[tri[:, 1]], px[tri[:, 2]], py[tri[:, 2]]
+    det = (bx - ax) * (cy - ay) - (cx - ax) * (by - ay)
+    out = np.full(len(points), -1)
+    for i, (X, Y) in enumerate(points):
+        l1 = ((bx - X) * (cy - Y) - (cx - X) * (by - Y)) / det
+        l2 = ((cx - X) * (ay - Y) - (ax - X) * (cy - Y)) / det
+        m = np.minimum(np.minimum(l1, l2), 1.0 - l1 - l2)
+        k = int(np.argmax(m))
+        if m[k] >= -1e-9:
+            out[i] = k
+    return out
+
+
+def check_stress(stress, ux, uy, g):
+    """The picture colours every element by its `stress` (solver.rs:524-533: sqrt(sx^2 + sy^2), negative where
+    sx + sy < 1) through matplotlib's "coolwarm" between the smallest and the largest value.  Those two depend on the
+    single most stressed corner triangle, i.e. on the triangulation, so only the ORDER is comparable: the rank
+    correlation between the picture's colour (red minus blue, monotone in the plotted value) on a 12.5-unit grid and
+    our stress in the element under each grid point.  Measured: 0.980 with the reference's rule; 0.947 if the sign is
+    dropped, 0.942 for a von Mises stress."""
+    from scipy.stats import spearmanr
+    colour = np.array(PICTURE["panels"]["solved"]["red_minus_blue"])
+    tri = np.stack([g["n0"], g["n1"], g["n2"]], 1).astype(np.int64)
+    el = elements_at(colour[:, :2], g["x"] + ux, g["y"] + uy, tri)
+    inside = el >= 0
+    assert len(colour) >= 1500 and inside.mean() >= 0.99
+    rho = spearmanr(colour[inside, 2], stress[el[inside]]).statistic
+    assert rho >= 0.97, rho
+    assert spearmanr(colour[inside, 2], np.abs(stress[el[inside]])).statistic <= rho - 0.02     # the sign rule is visible
+
+
 def test_oracle_solution_lies_on_the_reference_picture():
     from oracle import oracle as O
     g, mesh, meta = example()
     res = O.run(O.Mesh(mesh), meta, O.cg_options(), dense=False)       # the reference's solver semantics
     check(res["ux"], res["uy"], g)
+    check_stress(res["stress"], res["ux"], res["uy"], g)
     # ... and the committed fixture is that solution
     assert np.linalg.norm(res["ux"] - g["ux"]) <= 1e-9 * np.linalg.norm(g["ux"])
 
@@ -101,5 +136,6 @@ def test_gpu_solution_lies_on_the_reference_picture(ctx):
     g, mesh, meta = example()
     sol = solver.solve_soa(mesh, meta, ctx, _lib.default_options(compat=1))
     check(sol.ux, sol.uy, g)
+    check_stress(sol.stress, sol.ux, sol.uy, g)
     sol = solver.solve_soa(mesh, meta, ctx, _lib.default_options())   # the library's default solver, same picture
     check(sol.ux, sol.uy, g)
