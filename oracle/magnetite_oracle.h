@@ -19,9 +19,10 @@
  * reference's own documentation (under-the-hood.md), an independent
  * numpy/scipy restatement (oracle/reference_semantics.py) and — to the
  * resolution of a picture, about 1 % of the displacement, nowhere near
- * rounding level — the one output of its own solver the reference publishes:
- * the true-scale deformed outline of examples/linkedin-logo/output.png
- * (tests/test_reference_picture.py, tests/golden/measure_reference_picture.py).
+ * rounding level — the outputs of its own solver the reference publishes:
+ * the true-scale deformed outlines of examples/linkedin-logo/output.png and
+ * media/tensilve-results.png (tests/test_reference_picture.py,
+ * tests/golden/measure_reference_picture.py).
  *
  * All arithmetic is fp64, compiled with -ffp-contract=off so that every
  * multiply and add is rounded separately, as rustc does.

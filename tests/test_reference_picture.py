@@ -1,17 +1,20 @@
-"""The one numeric output of its own solver the reference publishes: the TRUE-SCALE deformed shape of its
-linkedin-logo example (examples/linkedin-logo/output.png, drawn by scripts/plot.py:143-147 at (x + ux, y + uy)).
+"""The numeric outputs of its own solver the reference publishes: the TRUE-SCALE deformed shapes of two of its
+examples — examples/linkedin-logo/output.png (readme.md:28-30) and media/tensilve-results.png (the tensile example,
+BASELINE config 1) — drawn by scripts/plot.py:143-147 at (x + ux, y + uy) beside the undeformed mesh.
 
-tests/golden/measure_reference_picture.py read that picture in the build container and committed what it shows —
-the intervals the solved and the initial model cover along horizontal and vertical lines every 25 units, one pixel
-= 0.73 units — as tests/golden/reference_linkedin_picture.json.  Here the same example (same outline, same
-input.json, the stand-in mesher's triangulation instead of gmsh's: tests/golden/example_linkedin.npz) is solved by
-the oracle (CPU) and by the library (GPU) and the deformed outline is laid over the reference's.
+tests/golden/measure_reference_picture.py read those pictures in the build container and committed what they show —
+the intervals the solved and the initial model cover along horizontal and vertical lines, to one pixel (0.73 units
+of the 628-unit logo; 0.016 x 0.023 units of the 22 x 9 tensile bar) — as tests/golden/reference_*_picture.json.
+Here the same examples (same outlines, same input.json, the stand-in mesher's triangulation instead of gmsh's:
+tests/golden/example_*.npz) are solved by the oracle (CPU) and by the library (GPU) and the deformed outline is laid
+over the reference's.
 
-What this pins, to ~1 % of the 150-unit displacement: the boundary-rule semantics (which nodes are held, which are
+What this pins, to 1-2 % of the displacements: the boundary-rule semantics (which nodes are held, which are
 pulled), plane STRESS (plane strain would contract the waist by 0.49 instead of 0.33 of the stretch), the assembly
-and the solve, signs and axes, and that nothing is magnified; the colours pin the ORDER of the element stresses and
-the sign rule of solver.rs:524-530.  It cannot pin rounding-level arithmetic — the oracle
-header's "parity unpinned" stays true for that — but it is an output of the reference itself.
+and the solve — for the tensile example on the all-clockwise mesh check_ccw produces (mesher.rs:522-526: a negative
+definite K) — signs and axes, and that nothing is magnified; the colours of the linkedin picture pin the
+ORDER of the element stresses and the sign rule of solver.rs:524-530.  It cannot pin rounding-level arithmetic — the
+oracle header's "parity unpinned" stays true for that — but these are outputs of the reference itself.
 """
 import json
 from pathlib import Path
@@ -23,15 +26,17 @@ from magnetite_b200 import meshgen
 from magnetite_b200.datatypes import MeshSoA
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
-PICTURE = json.loads((GOLDEN / "reference_linkedin_picture.json").read_text())
-UNITS_PER_PIXEL = 1.0 / PICTURE["panels"]["solved"]["pixels_per_unit"]
-# an edge in the picture: half a pixel of anti-aliasing counted as model + half a pixel of sampling + the two
-# triangulations' different boundary vertices on curved edges
-TOL = 2.0 * UNITS_PER_PIXEL + 0.4
+NAMES = ["linkedin", "tensile"]
+PICTURES = {n: json.loads((GOLDEN / f"reference_{n}_picture.json").read_text()) for n in NAMES}
+# Distances are measured in PIXELS of the picture (the tensile plot's axes are not to the same scale).  An edge in
+# the picture: half a pixel of anti-aliasing counted as model + half a pixel of sampling + the two triangulations'
+# different boundary vertices on curved edges.  Measured: 1.85 (logo) / 1.77 (bar) for the undeformed outlines.
+TOL_PX = 3.0
+TEETH_PX = 4.0
 
 
-def example():
-    g = np.load(GOLDEN / "example_linkedin.npz")
+def example(name):
+    g = np.load(GOLDEN / f"example_{name}.npz")
     mesh = MeshSoA(g["x"], g["y"], g["n0"], g["n1"], g["n2"], g["bc_ux"], g["bc_uy"], g["bc_fx"], g["bc_fy"], g["known"])
     meta = meshgen.EXAMPLE_MATERIAL.__class__(*g["material"])
     return g, mesh, meta
@@ -48,43 +53,45 @@ def outline_edges(tri):
 def picture_points(panel):
     """Every point where a line of the picture enters or leaves the model: (x, y) on the reference's outline."""
     pts = []
-    for line in PICTURE["panels"][panel]["along_y"].values():
+    for line in panel["along_y"]:
         pts += [(v, line["at"]) for iv in line["intervals"] for v in iv]
-    for line in PICTURE["panels"][panel]["along_x"].values():
+    for line in panel["along_x"]:
         pts += [(line["at"], v) for iv in line["intervals"] for v in iv]
     return np.array(pts)
 
 
-def distance_to_outline(points, px, py, edges):
-    """Distance of every point to the nearest outline segment."""
-    a = np.stack([px[edges[:, 0]], py[edges[:, 0]]], 1)[None]        # (1, S, 2)
-    b = np.stack([px[edges[:, 1]], py[edges[:, 1]]], 1)[None]
-    p = points[:, None, :]                                            # (P, 1, 2)
+def misfit(panel, px, py, tri):
+    """(number of picture points, their largest and mean distance to our outline) in pixels of the picture."""
+    scale = np.array([panel["pixels_per_unit_x"], panel["pixels_per_unit_y"]])
+    edges = outline_edges(tri)
+    a = (np.stack([px[edges[:, 0]], py[edges[:, 0]]], 1) * scale)[None]        # (1, S, 2)
+    b = (np.stack([px[edges[:, 1]], py[edges[:, 1]]], 1) * scale)[None]
+    p = (picture_points(panel) * scale)[:, None, :]                            # (P, 1, 2)
     ab = b - a
     t = np.clip(((p - a) * ab).sum(2) / np.maximum((ab * ab).sum(2), 1e-300), 0.0, 1.0)
-    return np.linalg.norm(p - (a + t[..., None] * ab), axis=2).min(1)
-
-
-def misfit(panel, px, py, tri):
-    """(number of picture points, their largest and mean distance to our outline)."""
-    d = distance_to_outline(picture_points(panel), px, py, outline_edges(tri))
+    d = np.linalg.norm(p - (a + t[..., None] * ab), axis=2).min(1)
     return len(d), float(d.max()), float(d.mean())
 
 
-def check(ux, uy, g):
+def check(name, ux, uy, g):
+    pic = PICTURES[name]["panels"]
     tri = np.stack([g["n0"], g["n1"], g["n2"]], 1).astype(np.int64)
     x, y = g["x"], g["y"]
     # the geometry first: the undeformed outline is the picture's "Initial Model"
-    n0, worst0, mean0 = misfit("initial", x, y, tri)
-    assert n0 >= 200 and worst0 <= TOL and mean0 <= 0.5 * TOL, (n0, worst0, mean0)
-    # the solution: every point of the reference's deformed outline lies on ours, as closely as the undeformed one
-    # (measured: 254 points, worst 1.46 / mean 0.58 units against 1.35 / 0.57 for the geometry alone)
-    n, worst, mean = misfit("solved", x + ux, y + uy, tri)
-    assert n >= 240 and worst <= TOL and mean <= mean0 + 0.1, (n, worst, mean)
-    # and the comparison has teeth: no lateral contraction, plane strain's contraction (0.49 / 0.33 of it), a
-    # 2 % error of the stretch or a magnified plot do not fit
-    for fx, fy in ((0.0, 1.0), (0.49 / 0.33, 1.0), (1.1, 1.0), (1.0, 0.98), (1.02, 1.02)):
-        assert misfit("solved", x + fx * ux, y + fy * uy, tri)[1] > 1.25 * TOL, (fx, fy)
+    n0, worst0, mean0 = misfit(pic["initial"], x, y, tri)
+    assert n0 >= 200 and worst0 <= TOL_PX, (n0, worst0, mean0)
+    # the solution: every point of the reference's deformed outline lies on ours, about as closely as the undeformed
+    # one (measured, pixels: logo 254 points, worst 2.01 / mean 0.79 against 1.85 / 0.78 for the geometry alone;
+    # bar 210 points, 2.48 / 1.04 against 1.77 / 0.89)
+    n, worst, mean = misfit(pic["solved"], x + ux, y + uy, tri)
+    assert n >= 200 and worst <= TOL_PX and mean <= mean0 + 0.25, (n, worst, mean)
+    # and the comparison has teeth: no deformation across the pull, plane strain's contraction (0.49 / 0.33 of plane
+    # stress's), a 2 % error of the stretch or a magnified plot do not fit
+    across = (0.0, 1.0) if name == "linkedin" else (1.0, 0.0)                 # the logo is pulled in y, the bar in x
+    strain = (0.49 / 0.33, 1.0) if name == "linkedin" else (1.0, 0.49 / 0.33)
+    along = (1.0, 0.98) if name == "linkedin" else (0.98, 1.0)
+    for fx, fy in (across, strain, along, (1.02, 1.02)):
+        assert misfit(pic["solved"], x + fx * ux, y + fy * uy, tri)[1] > TEETH_PX, (fx, fy)
 
 
 def elements_at(points, px, py, tri):
@@ -110,7 +117,7 @@ def check_stress(stress, ux, uy, g):
     our stress in the element under each grid point.  Measured: 0.980 with the reference's rule; 0.947 if the sign is
     dropped, 0.942 for a von Mises stress."""
     from scipy.stats import spearmanr
-    colour = np.array(PICTURE["panels"]["solved"]["red_minus_blue"])
+    colour = np.array(PICTURES["linkedin"]["panels"]["solved"]["red_minus_blue"])
     tri = np.stack([g["n0"], g["n1"], g["n2"]], 1).astype(np.int64)
     el = elements_at(colour[:, :2], g["x"] + ux, g["y"] + uy, tri)
     inside = el >= 0
@@ -120,22 +127,26 @@ def check_stress(stress, ux, uy, g):
     assert spearmanr(colour[inside, 2], np.abs(stress[el[inside]])).statistic <= rho - 0.02     # the sign rule is visible
 
 
-def test_oracle_solution_lies_on_the_reference_picture():
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_solution_lies_on_the_reference_picture(name):
     from oracle import oracle as O
-    g, mesh, meta = example()
+    g, mesh, meta = example(name)
     res = O.run(O.Mesh(mesh), meta, O.cg_options(), dense=False)       # the reference's solver semantics
-    check(res["ux"], res["uy"], g)
-    check_stress(res["stress"], res["ux"], res["uy"], g)
+    check(name, res["ux"], res["uy"], g)
+    if name == "linkedin":
+        check_stress(res["stress"], res["ux"], res["uy"], g)
     # ... and the committed fixture is that solution
     assert np.linalg.norm(res["ux"] - g["ux"]) <= 1e-9 * np.linalg.norm(g["ux"])
 
 
 @pytest.mark.gpu
-def test_gpu_solution_lies_on_the_reference_picture(ctx):
+@pytest.mark.parametrize("name", NAMES)
+def test_gpu_solution_lies_on_the_reference_picture(ctx, name):
     from magnetite_b200 import _lib, solver
-    g, mesh, meta = example()
+    g, mesh, meta = example(name)
     sol = solver.solve_soa(mesh, meta, ctx, _lib.default_options(compat=1))
-    check(sol.ux, sol.uy, g)
-    check_stress(sol.stress, sol.ux, sol.uy, g)
+    check(name, sol.ux, sol.uy, g)
+    if name == "linkedin":
+        check_stress(sol.stress, sol.ux, sol.uy, g)
     sol = solver.solve_soa(mesh, meta, ctx, _lib.default_options())   # the library's default solver, same picture
-    check(sol.ux, sol.uy, g)
+    check(name, sol.ux, sol.uy, g)
