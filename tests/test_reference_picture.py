@@ -92,6 +92,14 @@ def check(name, ux, uy, g):
     along = (1.0, 0.98) if name == "linkedin" else (0.98, 1.0)
     for fx, fy in (across, strain, along, (1.02, 1.02)):
         assert misfit(pic["solved"], x + fx * ux, y + fy * uy, tri)[1] > TEETH_PX, (fx, fy)
+    # sharper: scale our displacement along the pull by f — the picture is explained best by f = 1.00 +- 0.01 (the
+    # mean distance is a V around it: logo 1.46 / 0.79 / 1.10 px at f = 0.98 / 1.00 / 1.02, bar 1.70 / 1.04 / 1.62); for
+    # the logo the same holds for the lateral contraction (the bar's is 5 pixels in all and too small to weigh)
+    factors = [0.97, 0.98, 0.99, 1.0, 1.01, 1.02, 1.03]
+    pulls = {"linkedin": [(0, 1), (1, 0)], "tensile": [(1, 0)]}[name]
+    for ax, ay in pulls:
+        means = [misfit(pic["solved"], x + (f if ax else 1.0) * ux, y + (f if ay else 1.0) * uy, tri)[2] for f in factors]
+        assert 0.99 <= factors[int(np.argmin(means))] <= 1.01, (ax, ay, means)
 
 
 def elements_at(points, px, py, tri):
