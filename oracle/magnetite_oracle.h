@@ -20,8 +20,9 @@
  * numpy/scipy restatement (oracle/reference_semantics.py) and — to the
  * resolution of a picture, about 1 % of the displacement, nowhere near
  * rounding level — the outputs of its own solver the reference publishes:
- * the true-scale deformed outlines of examples/linkedin-logo/output.png and
- * media/tensilve-results.png (tests/test_reference_picture.py,
+ * the true-scale deformed outlines of examples/linkedin-logo/output.png,
+ * media/tensilve-results.png and examples/cover-eample/output.png
+ * (tests/test_reference_picture.py,
  * tests/golden/measure_reference_picture.py).
  *
  * All arithmetic is fp64, compiled with -ffp-contract=off so that every

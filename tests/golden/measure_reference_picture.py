@@ -1,7 +1,7 @@
 """Measures the numeric outputs the reference publishes of its own solver: the TRUE-SCALE deformed shapes in
-/root/reference/examples/linkedin-logo/output.png (readme.md:28-30) and /root/reference/media/tensilve-results.png
-(the tensile example), both drawn by scripts/plot.py:143-147 at (x + ux, y + uy), no magnification, beside the
-undeformed mesh.
+/root/reference/examples/linkedin-logo/output.png (readme.md:28-30), /root/reference/media/tensilve-results.png
+(the tensile example) and /root/reference/examples/cover-eample/output.png (readme.md:1), all drawn by
+scripts/plot.py:143-147 at (x + ux, y + uy), no magnification, the first two beside the undeformed mesh.
 
 Nothing of the pictures is copied: this script reads them where they lie, finds the gridlines of the two panels
 (matplotlib's seaborn-v0_8 style: white lines on a (234,234,242) background; which values the first lines carry is
@@ -32,6 +32,13 @@ PICTURES = {
                      lines_y=np.arange(-650.0, 176.0, 25.0), lines_x=np.arange(0.0, 651.0, 25.0), colour_step=12.5),
     "tensile": dict(path="media/tensilve-results.png", x0=-10.0, dx=5.0, y0=4.0, dy=2.0,
                     lines_y=np.arange(-4.75, 4.76, 0.25), lines_x=np.arange(-11.5, 14.51, 0.5), colour_step=None),
+    # The cover picture is cropped to the solved panel, tick labels cut away.  Its gridlines are 412.4 px apart in x and
+    # 82.5 px in y; the clamped bottom edge and the pulled top band keep ux = 0 (input.json), so the model stays 479.66
+    # units wide there, which is 1978 px: 4.124 px per unit, i.e. lines every 100 units in x and (equal aspect) every 20
+    # in y.  The line through the model's left edge is x = 0; the clamped bottom edge (y = -91.05) lies 11 units under
+    # the lowest line, so the lines are y = 0, -20, ... -80 from the top.
+    "cover": dict(path="examples/cover-eample/output.png", x0=0.0, dx=100.0, y0=0.0, dy=20.0, panels=("solved",),
+                  lines_y=np.arange(-90.0, 10.1, 2.5), lines_x=np.arange(5.0, 480.0, 10.0), colour_step=None),
 }
 
 
@@ -72,10 +79,11 @@ def measure(name, cfg):
     row_rng = ranges(is_bg.sum(1) > 0.05 * W, 50)
     col_rng = ranges(is_bg.sum(0) > 0.05 * H, 50)
     boxes = [(r, c) for r in row_rng for c in col_rng]                  # "Solved Model" is the first panel (left / top)
-    assert len(boxes) == 2, (row_rng, col_rng)
+    panels = cfg.get("panels", ("solved", "initial"))
+    assert len(boxes) == len(panels), (row_rng, col_rng)
     result = {"source": f"{cfg['path']} of kyle-tennison/Magnetite (the reference's own run of its example)",
               "made_by": "tests/golden/measure_reference_picture.py", "picture_size": [W, H], "panels": {}}
-    for panel_name, ((r0, r1), (c0, c1)) in zip(("solved", "initial"), boxes):
+    for panel_name, ((r0, r1), (c0, c1)) in zip(panels, boxes):
         # gridlines: white runs in the background strip under / left of the model
         # (centres averaged over a band of 8 pixel lines: a line is 2-3 pixels wide and not pixel-aligned)
         band_v = [[0.5 * (a + b) + c0 for a, b in runs_of(is_white[r, c0:c1 + 1]) if b - a < 6] for r in range(r1 - 11, r1 - 3)]
@@ -125,7 +133,7 @@ def measure(name, cfg):
         result["panels"][panel_name] = panel
     out = HERE / f"reference_{name}_picture.json"
     out.write_text(json.dumps(result, separators=(",", ":")) + "\n")
-    s, i = result["panels"]["solved"], result["panels"]["initial"]
+    s, i = result["panels"]["solved"], result["panels"].get("initial", {"along_y": [], "along_x": []})
     print(f"{out.name}: {len(s['along_y'])} + {len(s['along_x'])} lines of the solved model, "
           f"{len(i['along_y'])} + {len(i['along_x'])} of the initial one, {s['pixels_per_unit_x']} x {s['pixels_per_unit_y']} "
           f"px per unit, {len(s.get('red_minus_blue', []))} colour samples")

@@ -1,6 +1,7 @@
-"""The numeric outputs of its own solver the reference publishes: the TRUE-SCALE deformed shapes of two of its
-examples — examples/linkedin-logo/output.png (readme.md:28-30) and media/tensilve-results.png (the tensile example,
-BASELINE config 1) — drawn by scripts/plot.py:143-147 at (x + ux, y + uy) beside the undeformed mesh.
+"""The numeric outputs of its own solver the reference publishes: the TRUE-SCALE deformed shapes of its three
+examples — examples/linkedin-logo/output.png (readme.md:28-30), media/tensilve-results.png (the tensile example,
+BASELINE config 1) and examples/cover-eample/output.png (readme.md:1) — drawn by scripts/plot.py:143-147 at
+(x + ux, y + uy), the first two beside the undeformed mesh.
 
 tests/golden/measure_reference_picture.py read those pictures in the build container and committed what they show —
 the intervals the solved and the initial model cover along horizontal and vertical lines, to one pixel (0.73 units
@@ -26,7 +27,7 @@ from magnetite_b200 import meshgen
 from magnetite_b200.datatypes import MeshSoA
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
-NAMES = ["linkedin", "tensile"]
+NAMES = ["linkedin", "tensile", "cover"]
 PICTURES = {n: json.loads((GOLDEN / f"reference_{n}_picture.json").read_text()) for n in NAMES}
 # Distances are measured in PIXELS of the picture (the tensile plot's axes are not to the same scale).  An edge in
 # the picture: half a pixel of anti-aliasing counted as model + half a pixel of sampling + the two triangulations'
@@ -61,7 +62,7 @@ def picture_points(panel):
 
 
 def misfit(panel, px, py, tri):
-    """(number of picture points, their largest and mean distance to our outline) in pixels of the picture."""
+    """(number of picture points, their largest, mean and 99th-percentile distance to our outline) in pixels."""
     scale = np.array([panel["pixels_per_unit_x"], panel["pixels_per_unit_y"]])
     edges = outline_edges(tri)
     a = (np.stack([px[edges[:, 0]], py[edges[:, 0]]], 1) * scale)[None]        # (1, S, 2)
@@ -70,20 +71,22 @@ def misfit(panel, px, py, tri):
     ab = b - a
     t = np.clip(((p - a) * ab).sum(2) / np.maximum((ab * ab).sum(2), 1e-300), 0.0, 1.0)
     d = np.linalg.norm(p - (a + t[..., None] * ab), axis=2).min(1)
-    return len(d), float(d.max()), float(d.mean())
+    return len(d), float(d.max()), float(d.mean()), float(np.percentile(d, 99))
 
 
 def check(name, ux, uy, g):
     pic = PICTURES[name]["panels"]
     tri = np.stack([g["n0"], g["n1"], g["n2"]], 1).astype(np.int64)
     x, y = g["x"], g["y"]
+    if name == "cover":
+        return check_cover(pic["solved"], x, y, ux, uy, tri)
     # the geometry first: the undeformed outline is the picture's "Initial Model"
-    n0, worst0, mean0 = misfit(pic["initial"], x, y, tri)
+    n0, worst0, mean0, _ = misfit(pic["initial"], x, y, tri)
     assert n0 >= 200 and worst0 <= TOL_PX, (n0, worst0, mean0)
     # the solution: every point of the reference's deformed outline lies on ours, about as closely as the undeformed
     # one (measured, pixels: logo 254 points, worst 2.01 / mean 0.79 against 1.85 / 0.78 for the geometry alone;
     # bar 210 points, 2.48 / 1.04 against 1.77 / 0.89)
-    n, worst, mean = misfit(pic["solved"], x + ux, y + uy, tri)
+    n, worst, mean, _ = misfit(pic["solved"], x + ux, y + uy, tri)
     assert n >= 200 and worst <= TOL_PX and mean <= mean0 + 0.25, (n, worst, mean)
     # and the comparison has teeth: no deformation across the pull, plane strain's contraction (0.49 / 0.33 of plane
     # stress's), a 2 % error of the stretch or a magnified plot do not fit
@@ -100,6 +103,18 @@ def check(name, ux, uy, g):
     for ax, ay in pulls:
         means = [misfit(pic["solved"], x + (f if ax else 1.0) * ux, y + (f if ay else 1.0) * uy, tri)[2] for f in factors]
         assert 0.99 <= factors[int(np.argmin(means))] <= 1.01, (ax, ay, means)
+
+
+def check_cover(solved, x, y, ux, uy, tri):
+    """The cover picture (readme.md:1) is cropped to the solved panel: no undeformed panel separates what the two
+    meshers make of the letters' outlines from the deformation, and 2 of its 960 points sit 7 pixels off such a
+    feature — so the 99th percentile stands in for the worst point (measured 1.80 px, mean 0.84), and the pull (10
+    units = 41 pixels, lateral motion up to 5 units) is resolved to about 10 %: a weaker pin than the other two
+    pictures, of a third geometry."""
+    n, worst, mean, p99 = misfit(solved, x + ux, y + uy, tri)
+    assert n >= 900 and p99 <= TOL_PX and mean <= 1.0 and worst <= 9.0, (n, worst, mean, p99)
+    for fx, fy in ((1.0, 0.9), (1.0, 1.1), (0.0, 1.0), (1.5, 1.0), (1.0, 0.0)):
+        assert misfit(solved, x + fx * ux, y + fy * uy, tri)[3] > TEETH_PX, (fx, fy)
 
 
 def elements_at(points, px, py, tri):
