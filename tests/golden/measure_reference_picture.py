@@ -7,9 +7,8 @@ Nothing of the pictures is copied: this script reads them where they lie, finds 
 (matplotlib's seaborn-v0_8 style: white lines on a (234,234,242) background; which values the first lines carry is
 read off the tick labels by eye and written into PICTURES below — the undeformed panel, whose geometry is known,
 checks it), and writes the intervals the model covers along horizontal and vertical lines, for both panels, into
-tests/golden/reference_<name>_picture.json: a few hundred numbers with a resolution of one pixel.  For the
-linkedin picture also the stress colour on a 12.5-unit grid (red minus blue of the "coolwarm" face colour, a monotone
-function of the plotted stress).  tests/test_reference_picture.py compares the oracle's (CPU) and the library's (GPU)
+tests/golden/reference_<name>_picture.json: a few hundred numbers with a resolution of one pixel — and the face
+colour of the solved model on a grid (a monotone function of the plotted element stress).  tests/test_reference_picture.py compares the oracle's (CPU) and the library's (GPU)
 solutions of the same examples with them.
 
     python tests/golden/measure_reference_picture.py        # needs /root/reference and Pillow
@@ -31,14 +30,14 @@ PICTURES = {
     "linkedin": dict(path="examples/linkedin-logo/output.png", x0=0.0, dx=100.0, y0=100.0, dy=100.0,
                      lines_y=np.arange(-650.0, 176.0, 25.0), lines_x=np.arange(0.0, 651.0, 25.0), colour_step=12.5),
     "tensile": dict(path="media/tensilve-results.png", x0=-10.0, dx=5.0, y0=4.0, dy=2.0,
-                    lines_y=np.arange(-4.75, 4.76, 0.25), lines_x=np.arange(-11.5, 14.51, 0.5), colour_step=None),
+                    lines_y=np.arange(-4.75, 4.76, 0.25), lines_x=np.arange(-11.5, 14.51, 0.5), colour_step=0.4),
     # The cover picture is cropped to the solved panel, tick labels cut away.  Its gridlines are 412.4 px apart in x and
     # 82.5 px in y; the clamped bottom edge and the pulled top band keep ux = 0 (input.json), so the model stays 479.66
     # units wide there, which is 1978 px: 4.124 px per unit, i.e. lines every 100 units in x and (equal aspect) every 20
     # in y.  The line through the model's left edge is x = 0; the clamped bottom edge (y = -91.05) lies 11 units under
     # the lowest line, so the lines are y = 0, -20, ... -80 from the top.
     "cover": dict(path="examples/cover-eample/output.png", x0=0.0, dx=100.0, y0=0.0, dy=20.0, panels=("solved",),
-                  lines_y=np.arange(-90.0, 10.1, 2.5), lines_x=np.arange(5.0, 480.0, 10.0), colour_step=None),
+                  lines_y=np.arange(-90.0, 10.1, 2.5), lines_x=np.arange(5.0, 480.0, 10.0), colour_step=4.0),
 }
 
 
@@ -115,10 +114,11 @@ def measure(name, cfg):
                     panel["along_x"].append({"at": round(float(x_of(c + 0.5)), 4),
                                              "intervals": [[b, a] for a, b in iv][::-1]})      # ascending y
         if panel_name == "solved" and cfg["colour_step"]:
-            # the stress colours (scripts/plot.py:136-141,154-158: cmap "coolwarm" over [min stress, max stress], faces
-            # drawn with alpha 0.7): on a grid, where the 7x7 pixel patch around the point is all model, the median
-            # colour of its brighter half (the darker half is the black mesh lines), un-blended from the background,
-            # as red minus blue — a monotone function of the colormap parameter, hence of the stress
+            # the stress colours (scripts/plot.py:136-141,154-158: the --cmap colormap over [min stress, max stress],
+            # faces drawn with alpha 0.7): on a grid, where the 7x7 pixel patch around the point is all model, the
+            # median colour of its brighter half (the darker half is the black mesh lines), un-blended from the
+            # background.  The default "coolwarm" of the linkedin picture is monotone in red minus blue, the dark-to-
+            # bright maps of the other two in red — monotone functions of the plotted stress.
             colour, step = [], cfg["colour_step"]
             for Y in np.arange(y_of(r1) - y_of(r1) % step, y_of(r0), step):
                 for X in np.arange(x_of(c0) - x_of(c0) % step, x_of(c1), step):
@@ -128,15 +128,15 @@ def measure(name, cfg):
                     patch = im[r - 3:r + 4, c - 3:c + 4].reshape(-1, 3).astype(float)
                     lum = patch.sum(1)
                     rgb = (np.median(patch[lum >= np.percentile(lum, 50)], axis=0) - 0.3 * BACKGROUND) / 0.7
-                    colour.append([round(float(x_of(c + 0.5)), 2), round(float(y_of(r + 0.5)), 2), round(float(rgb[0] - rgb[2]), 1)])
-            panel["red_minus_blue"] = colour
+                    colour.append([round(float(x_of(c + 0.5)), 3), round(float(y_of(r + 0.5)), 3)] + [round(float(v), 1) for v in rgb])
+            panel["face_rgb"] = colour
         result["panels"][panel_name] = panel
     out = HERE / f"reference_{name}_picture.json"
     out.write_text(json.dumps(result, separators=(",", ":")) + "\n")
     s, i = result["panels"]["solved"], result["panels"].get("initial", {"along_y": [], "along_x": []})
     print(f"{out.name}: {len(s['along_y'])} + {len(s['along_x'])} lines of the solved model, "
           f"{len(i['along_y'])} + {len(i['along_x'])} of the initial one, {s['pixels_per_unit_x']} x {s['pixels_per_unit_y']} "
-          f"px per unit, {len(s.get('red_minus_blue', []))} colour samples")
+          f"px per unit, {len(s.get('face_rgb', []))} colour samples")
 
 
 if __name__ == "__main__":

@@ -13,8 +13,8 @@ over the reference's.
 What this pins, to 1-2 % of the displacements: the boundary-rule semantics (which nodes are held, which are
 pulled), plane STRESS (plane strain would contract the waist by 0.49 instead of 0.33 of the stretch), the assembly
 and the solve — for the tensile example on the all-clockwise mesh check_ccw produces (mesher.rs:522-526: a negative
-definite K) — signs and axes, and that nothing is magnified; the colours of the linkedin picture pin the
-ORDER of the element stresses and the sign rule of solver.rs:524-530.  It cannot pin rounding-level arithmetic — the
+definite K) — signs and axes, and that nothing is magnified; the face colours pin the ORDER of the element
+stresses and the sign rule of solver.rs:524-530.  It cannot pin rounding-level arithmetic — the
 oracle header's "parity unpinned" stays true for that — but these are outputs of the reference itself.
 """
 import json
@@ -132,22 +132,25 @@ def elements_at(points, px, py, tri):
     return out
 
 
-def check_stress(stress, ux, uy, g):
-    """The picture colours every element by its `stress` (solver.rs:524-533: sqrt(sx^2 + sy^2), negative where
-    sx + sy < 1) through matplotlib's "coolwarm" between the smallest and the largest value.  Those two depend on the
+def check_stress(name, stress, ux, uy, g):
+    """The pictures colour every element by its `stress` (solver.rs:524-533: sqrt(sx^2 + sy^2), negative where
+    sx + sy < 1) through a matplotlib colormap between the smallest and the largest value.  Those two depend on the
     single most stressed corner triangle, i.e. on the triangulation, so only the ORDER is comparable: the rank
-    correlation between the picture's colour (red minus blue, monotone in the plotted value) on a 12.5-unit grid and
-    our stress in the element under each grid point.  Measured: 0.980 with the reference's rule; 0.947 if the sign is
-    dropped, 0.942 for a von Mises stress."""
+    correlation between the face colour on a grid of points (a monotone function of the plotted value: red minus
+    blue for the logo's "coolwarm", red for the dark-to-bright maps of the other two) and our stress in the element
+    under each point.  Measured: logo 0.980 (0.947 if the sign is dropped, 0.942 for a von Mises stress), bar 0.979,
+    cover 0.975 (0.958 without the sign)."""
     from scipy.stats import spearmanr
-    colour = np.array(PICTURES["linkedin"]["panels"]["solved"]["red_minus_blue"])
+    rgb = np.array(PICTURES[name]["panels"]["solved"]["face_rgb"])
+    value = rgb[:, 2] - rgb[:, 4] if name == "linkedin" else rgb[:, 2]
     tri = np.stack([g["n0"], g["n1"], g["n2"]], 1).astype(np.int64)
-    el = elements_at(colour[:, :2], g["x"] + ux, g["y"] + uy, tri)
+    el = elements_at(rgb[:, :2], g["x"] + ux, g["y"] + uy, tri)
     inside = el >= 0
-    assert len(colour) >= 1500 and inside.mean() >= 0.99
-    rho = spearmanr(colour[inside, 2], stress[el[inside]]).statistic
-    assert rho >= 0.97, rho
-    assert spearmanr(colour[inside, 2], np.abs(stress[el[inside]])).statistic <= rho - 0.02     # the sign rule is visible
+    assert len(rgb) >= 900 and inside.mean() >= 0.99
+    rho = spearmanr(value[inside], stress[el[inside]]).statistic
+    assert rho >= 0.965, rho
+    if name != "tensile":                         # the bar is in tension nearly everywhere: 5 % negative elements
+        assert spearmanr(value[inside], np.abs(stress[el[inside]])).statistic <= rho - 0.01     # the sign rule is visible
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -156,8 +159,7 @@ def test_oracle_solution_lies_on_the_reference_picture(name):
     g, mesh, meta = example(name)
     res = O.run(O.Mesh(mesh), meta, O.cg_options(), dense=False)       # the reference's solver semantics
     check(name, res["ux"], res["uy"], g)
-    if name == "linkedin":
-        check_stress(res["stress"], res["ux"], res["uy"], g)
+    check_stress(name, res["stress"], res["ux"], res["uy"], g)
     # ... and the committed fixture is that solution
     assert np.linalg.norm(res["ux"] - g["ux"]) <= 1e-9 * np.linalg.norm(g["ux"])
 
@@ -169,7 +171,6 @@ def test_gpu_solution_lies_on_the_reference_picture(ctx, name):
     g, mesh, meta = example(name)
     sol = solver.solve_soa(mesh, meta, ctx, _lib.default_options(compat=1))
     check(name, sol.ux, sol.uy, g)
-    if name == "linkedin":
-        check_stress(sol.stress, sol.ux, sol.uy, g)
+    check_stress(name, sol.stress, sol.ux, sol.uy, g)
     sol = solver.solve_soa(mesh, meta, ctx, _lib.default_options())   # the library's default solver, same picture
     check(name, sol.ux, sol.uy, g)
