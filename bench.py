@@ -646,6 +646,21 @@ def run_ours(args):
                                 "reference_published_solve_s": published}
                 if not (example[key]["rel_l2_vs_oracle_fixture"] <= 1e-9):
                     failures.append(f"{key} differs from the oracle fixture: {example[key]['rel_l2_vs_oracle_fixture']:.3e}")
+                # the reference's own published result picture of this example (tests/test_reference_picture.py):
+                # distance, in pixels of the picture, of its deformed outline's points to the GPU solution's outline
+                try:
+                    if str(ROOT / "tests") not in sys.path:
+                        sys.path.insert(0, str(ROOT / "tests"))
+                    import test_reference_picture as TP
+                    tri = np.stack([g["n0"], g["n1"], g["n2"]], 1).astype(np.int64)
+                    n_pts, worst, mean, _ = TP.misfit(TP.PICTURES[fixture[8:]]["panels"]["solved"], g["x"] + sol.ux,
+                                                      g["y"] + sol.uy, tri)
+                    example[key]["reference_picture"] = {"outline_points": n_pts, "worst_px": worst, "mean_px": mean,
+                                                         "max_worst_px": TP.TOL_PX}
+                    if not (worst <= TP.TOL_PX):
+                        failures.append(f"{key}: the GPU solution's outline is {worst:.2f} px off the reference's picture")
+                except Exception as err:
+                    example[key]["reference_picture"] = {"error": str(err)}
             except Exception as err:
                 example[key] = {"error": str(err)}
         try:
